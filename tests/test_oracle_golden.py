@@ -1,0 +1,138 @@
+"""CPU: the oracle (oracle/teco_oracle.py) against the golden vectors produced by running the
+reference's own lib/*.py under the TF shim (tests/golden/make_golden.py).  Pins wiring."""
+import ast
+import os
+
+import numpy as np
+import torch
+
+from oracle import teco_oracle as O
+from tests.conftest import GOLDEN
+
+TOL = dict(rtol=2e-5, atol=2e-5)
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a, dtype=np.float32))
+
+
+def test_in_tree_resamplers_and_gaussdown():
+    g = _load("ops")
+    np.testing.assert_allclose(O.bicubic_four(_t(g["x"])).numpy(), g["bicubic_four"], **TOL)
+    np.testing.assert_allclose(O.upscale_four(_t(g["f"])).numpy(), g["upscale_four"], **TOL)
+    np.testing.assert_allclose(O.gauss_down_by4(_t(g["hr"])).numpy(), g["gauss_down"], **TOL)
+    np.testing.assert_allclose(O.deprocess(_t(g["x"])).numpy(), g["deprocess"], **TOL)
+    np.testing.assert_allclose(O.preprocess(_t(g["x"])).numpy(), g["preprocess"], **TOL)
+    # upscale_four "mimics the tensorflow bilinear-upscaling" (lib/ops.py:126): equals legacy resize
+    f = _t(g["f"])
+    np.testing.assert_allclose(O.resize_bilinear_legacy(f, f.shape[1] * 4, f.shape[2] * 4).numpy(),
+                               g["upscale_four"], **TOL)
+
+
+def test_generator_matches_reference_wiring():
+    for n in (3, 16):
+        g = _load("generator_n%d" % n)
+        p = O.init_generator(seed=int(g["seed"]), num_resblock=n, bias_std=float(g["bias_std"]))
+        out = O.generator_F(p, _t(g["inputs"]), n).numpy()
+        np.testing.assert_allclose(out, g["out"], rtol=1e-4, atol=1e-4)
+
+
+def test_fnet_matches_reference_wiring():
+    g = _load("fnet")
+    p = O.init_fnet(seed=int(g["seed"]), bias_std=float(g["bias_std"]))
+    np.testing.assert_allclose(O.fnet(p, _t(g["inputs"])).numpy(), g["out"], rtol=1e-4, atol=1e-4)
+
+
+def test_discriminator_matches_reference_wiring():
+    g = _load("discriminator")
+    p = O.init_discriminator(seed=int(g["seed"]), bias_std=float(g["bias_std"]))
+    prob, layers = O.discriminator_F(p, _t(g["inputs"]))
+    np.testing.assert_allclose(prob.numpy(), g["prob"], rtol=1e-4, atol=1e-4)
+    for i, l in enumerate(layers):
+        np.testing.assert_allclose(l.numpy(), g["layer%d" % i], rtol=1e-4, atol=1e-4)
+
+
+def test_vgg_matches_reference_wiring():
+    g = _load("vgg")
+    p = O.init_vgg19(seed=int(g["seed"]))
+    feats = O.vgg19_features(p, _t(g["inputs"]))
+    for i, k in enumerate(O.VGG_TAPS):
+        np.testing.assert_allclose(feats[k].numpy(), g["tap%d" % i], rtol=1e-4, atol=1e-5)
+
+
+def _teco_case(name):
+    g = _load(name)
+    ci = int(g["ci"])
+    fl = ast.literal_eval(str(g["flags"]))
+    FL = O.TrainFlags(**fl)
+    P = {}
+    P.update(O.init_generator(seed=61 + ci, num_resblock=FL.num_resblock, bias_std=0.05))
+    P.update(O.init_fnet(seed=71 + ci, bias_std=0.05))
+    P.update(O.init_discriminator(seed=81 + ci, bias_std=0.05))
+    if FL.vgg_scaling > 0:
+        P.update(O.init_vgg19(seed=91 + ci))
+    with torch.no_grad():
+        res = O.tecogan_forward(P, _t(g["r_inputs"]), _t(g["r_targets"]), FL, bool(g["gan"]))
+    assert [str(s) for s in g["update_list_name"]] == res["update_list_name"]
+    np.testing.assert_allclose(np.array([float(v) for v in res["update_list"]]), g["update_list"], rtol=2e-4, atol=1e-5)
+    T = res["gen_outputs"].shape[1]
+    np.testing.assert_allclose(res["gen_outputs"].reshape(-1, *res["gen_outputs"].shape[2:]).numpy(),
+                               g["gen_output"], rtol=1e-3, atol=2e-4)
+    return T
+
+
+def test_tecogan_pingpong_losses_match_reference_wiring():
+    assert _teco_case("teco_pp") == 5
+
+
+def test_tecogan_no_pingpong_backward_flow_branch():
+    assert _teco_case("teco_nopp") == 4
+
+
+def test_frvsr_losses_match_reference_wiring():
+    assert _teco_case("frvsr") == 3
+
+
+def test_calendar_fixture_and_warmup_order():
+    g = _load("calendar_lr")
+    assert g["crop32_u8"].shape == (10, 32, 32, 3) and g["full_u8"].shape == (7, 144, 180, 3)
+    assert [str(s) for s in g["order"][:5]] == ["0006.png", "0005.png", "0004.png", "0003.png", "0002.png"]
+    assert O.warmup_order(10)[:6] == [5, 4, 3, 2, 1, 0]
+
+
+def test_conv2d_transpose_is_gradient_of_same_stride2_conv():
+    torch.manual_seed(0)
+    x, w = torch.randn(2, 5, 7, 4), torch.randn(3, 3, 6, 4)
+    inp = torch.zeros(2, 10, 14, 6, requires_grad=True)
+    (gr,) = torch.autograd.grad(O.conv2d(inp, w, None, stride=2), inp, x)
+    assert (O.conv2d_transpose(x, w) - gr).abs().max().item() < 1e-5
+
+
+def test_warp_identity_and_integer_shift_and_clamp():
+    torch.manual_seed(1)
+    im = torch.rand(1, 6, 8, 3)
+    z = torch.zeros(1, 6, 8, 2)
+    assert torch.equal(O.dense_image_warp(im, z), im)
+    fl = z.clone(); fl[..., 0] = 1.0; fl[..., 1] = -2.0     # out[y,x] = im[y-1, x+2], border clamped
+    out = O.dense_image_warp(im, fl)
+    assert torch.allclose(out[0, 3, 2], im[0, 2, 4]) and torch.allclose(out[0, 0, 7], im[0, 0, 7])
+
+
+def test_inference_sequence_shapes_nonmultiple_of_8():
+    pg, pf = O.init_generator(num_resblock=2), O.init_fnet()
+    g = _load("calendar_lr")
+    frames = [torch.from_numpy(g["full_u8"][i, :44, :36].astype(np.float32) / 255.0) for i in range(3)]
+    outs = O.inference_sequence(pg, pf, frames, num_resblock=2)
+    assert outs[-1].shape == (176, 144, 3)
+
+
+def test_tf_adam_matches_closed_form_first_step():
+    p = {"a": torch.tensor([1.0, -2.0])}
+    opt = O.TFAdam(["a"], p, lr=0.1)
+    opt.apply(p, {"a": torch.tensor([0.5, -0.25])})
+    # step 1: m=(1-b1)g, v=(1-b2)g^2, lr_t = lr*sqrt(1-b2)/(1-b1) => delta = lr*g/(|g| + eps*sqrt(1-b2)) ~ lr*sign(g)
+    assert torch.allclose(p["a"], torch.tensor([0.9, -1.9]), atol=1e-5)
