@@ -1,0 +1,187 @@
+/*
+ * teco.h -- C ABI of libteco.so: hand-written sm_100a kernels for the TecoGAN recurrent
+ * video-SR hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * The reference (thunil/TecoGAN) has no FFI layer: its "operator API" is Python functions
+ * that build TensorFlow graph ops.  Each entry point below names the reference call site
+ * (file:line under /root/reference) whose TensorFlow/cuDNN arithmetic it replaces; the Python
+ * mirror in tecogan_b200/lib/{ops,frvsr,Teco}.py keeps the reference's function names and
+ * binds these symbols through ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - activations are NHWC, contiguous, with an explicit channel pitch where stated;
+ *  - weights use the TensorFlow layouts (conv: [kh,kw,Cin,Cout]; conv_transpose: [kh,kw,Cout,Cin]);
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing allocates;
+ *  - return 0 on success, a negative TECO_E_* code on failure; teco_last_error() gives the
+ *    thread-local message.  No exceptions cross the ABI.  There is no CPU fallback.
+ */
+#ifndef TECO_H_
+#define TECO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TECO_OK 0
+#define TECO_E_INVALID (-1)   /* bad shape / argument            -> Python ValueError   */
+#define TECO_E_CUDA (-2)      /* CUDA runtime / driver error     -> Python RuntimeError */
+#define TECO_E_UNSUPPORTED (-3)
+
+/* epilogue activations (reference: tf.nn.relu lib/frvsr.py:53; lrelu lib/ops.py:84-85 with
+ * alpha 0.2 lib/frvsr.py:8; tanh*24 lib/frvsr.py:39; sigmoid lib/Teco.py:72) */
+enum { TECO_ACT_NONE = 0, TECO_ACT_RELU = 1, TECO_ACT_LRELU02 = 2, TECO_ACT_TANH24 = 3, TECO_ACT_SIGMOID = 4 };
+
+const char* teco_last_error(void);
+int teco_version(void);
+/* Fills props[0..7] = {sm_count, cc_major, cc_minor, max_smem_optin, l2_bytes, 0,0,0}. */
+int teco_device_props(int device, int64_t* props);
+
+/* ---------------------------------------------------------------------------------------
+ * fp32 direct convolution (exact-parity path; also dgrad via flipped weights).
+ * Replaces slim.conv2d behind conv2() lib/ops.py:47-56 and, phase by phase, slim.conv2d_transpose
+ * behind conv2_tran() lib/ops.py:35-44.
+ *   y[n, oy*out_sy+out_oy, ox*out_sx+out_ox, co] =
+ *       post_scale * ( act( bias[co] + sum_{ky,kx,ci} x[n, oy*stride-pad_t+ky, ox*stride-pad_l+kx, ci]
+ *                                                    * w[ky,kx,ci,co] ) + res[same position] ) + post_shift
+ * out-of-range taps read zero (TF 'SAME').  bias / res may be NULL.
+ * ------------------------------------------------------------------------------------- */
+typedef struct teco_conv_desc {
+  int32_t N, H, W, Cin;          /* input tensor; in_cpitch >= Cin is its channel pitch      */
+  int32_t OH, OW, Cout;          /* logical output grid computed by this launch               */
+  int32_t KH, KW, stride, pad_t, pad_l;
+  int32_t out_H, out_W;          /* physical output tensor (y and res) spatial dims           */
+  int32_t out_sy, out_oy, out_sx, out_ox;
+  int32_t in_cpitch, out_cpitch; /* channel pitch (elements) of x and of y/res                */
+  int32_t act;
+  float post_scale, post_shift;
+} teco_conv_desc;
+
+int teco_conv2d_f32(const teco_conv_desc* d, const float* x, const float* w, const float* bias,
+                    const float* res, float* y, void* stream);
+
+/* Weight gradient of the same convolution: dw[ky,kx,ci,co] (+)= sum x(...) * dy(...), and
+ * optionally db[co] (+)= sum dy.  dy is addressed like y above.  accumulate!=0 adds into dw/db. */
+int teco_conv2d_wgrad_f32(const teco_conv_desc* d, const float* x, const float* dy, float* dw, float* db,
+                          int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * bf16 tensor-core convolution (tcgen05.mma kind::f16, fp32 accumulation in TMEM).
+ * 3x3, stride 1, SAME: the generator / FNet layers (lib/frvsr.py:5-41, 50-63, 79-80).
+ * x: NHWC bf16 with Cin (multiple of 16); y: NHWC bf16 with Cout channels.
+ * wpk: weights pre-packed by teco_pack_conv3x3_bf16 (UMMA canonical K-major core matrices).
+ * res (bf16, optional) is added after the activation; out_f32 (optional, [N,H,W,out_f32_c])
+ * receives post_scale*(value + res_f32) + post_shift for the first out_f32_c channels
+ * (used by the generator's output stage: + bicubic, *2-1  lib/frvsr.py:85-87).
+ * ------------------------------------------------------------------------------------- */
+typedef struct teco_tc_desc {
+  int32_t N, H, W, Cin, Cout;    /* Cin, Cout: padded channel counts (multiples of 16)       */
+  int32_t act;
+  int32_t mode;                  /* 0: conv3x3 s1 SAME; 1: conv_transpose 3x3 s2 SAME (4 phases) */
+  int32_t out_f32_c;             /* >0: also/only write fp32 output with this many channels  */
+  float post_scale, post_shift;
+} teco_tc_desc;
+
+int teco_pack_conv3x3_bf16(const float* w, int32_t cin, int32_t cout, int32_t cin_pad, int32_t cout_pad,
+                           int32_t transpose_layout, const int32_t* cin_perm, void* wpk, void* stream);
+int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad);
+int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void* wpk, const float* bias,
+                    const void* res, void* y, const float* res_f32, float* out_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Warp / resample family (HBM-bound).
+ * ------------------------------------------------------------------------------------- */
+/* tf.contrib.image.dense_image_warp (lib/Teco.py:120,140,224,254; main.py:215):
+ * out[n,y,x,c] = bilinear(img[n], (y - flow[n,y,x,0], x - flow[n,y,x,1])), border clamped. */
+int teco_warp_f32(const float* img, const float* flow, float* out, int32_t N, int32_t H, int32_t W, int32_t C,
+                  void* stream);
+/* gradients of the above: dimg (+)= scatter, dflow = d/dflow (zero where alpha is clipped). */
+int teco_warp_bwd_f32(const float* img, const float* flow, const float* dout, float* dimg, float* dflow,
+                      int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* Fused previous-HR feedback of the recurrence (main.py:201,209-216; lib/Teco.py:113,138-150):
+ *   flow_hr = upscale_four(4 * pad_symmetric(flow_lr))        lib/ops.py:126-163, main.py:212-213
+ *   warped  = dense_image_warp(pre_gen, flow_hr)              main.py:215
+ *   dst[n,y,x, ch_off + (dy*4+dx)*3 + c] = warped[n,4y+dy,4x+dx,c] * in_scale + in_shift   (space-to-depth 4)
+ * pre_gen: [N,4h,4w,3] fp32.  flow_lr: [N,fh,fw,2] fp32 with fh<=h, fw<=w (symmetric-padded to h,w).
+ * dst: [N,h,w,dst_cpitch] fp32 (dst_bf16==0) or bf16 (dst_bf16!=0).  warped_out (optional): fp32 [N,4h,4w,3]. */
+int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, float* warped_out,
+                        int32_t N, int32_t h, int32_t w, int32_t fh, int32_t fw, int32_t dst_cpitch,
+                        int32_t ch_off, int32_t dst_bf16, float in_scale, float in_shift, void* stream);
+
+/* upscale_four lib/ops.py:126-163 (legacy bilinear x4), `scale` multiplies the input (4.0 for flow). */
+int teco_upscale4_f32(const float* x, float* y, int32_t N, int32_t h, int32_t w, int32_t C, float scale, void* stream);
+/* bicubic_four lib/ops.py:166-212.  x read with channel pitch in_cpitch (first C channels). */
+int teco_bicubic4_f32(const float* x, float* y, int32_t N, int32_t h, int32_t w, int32_t C, int32_t in_cpitch,
+                      void* stream);
+/* tf.image.resize_images legacy bilinear to (oh,ow): lib/frvsr.py:21-22, lib/Teco.py:244. */
+int teco_resize_bilinear_f32(const float* x, float* y, int32_t N, int32_t h, int32_t w, int32_t C,
+                             int32_t oh, int32_t ow, void* stream);
+int teco_resize_bilinear_bwd_f32(const float* dy, float* dx, int32_t N, int32_t h, int32_t w, int32_t C,
+                                 int32_t oh, int32_t ow, void* stream);
+/* slim.max_pool2d 2x2 s2 VALID, lib/ops.py:92-93 (+ its gradient, routed to the first max). */
+int teco_maxpool2_f32(const float* x, float* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int teco_maxpool2_bwd_f32(const float* x, const float* dy, float* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                          void* stream);
+/* bf16 NHWC variants used between tensor-core layers of FNet */
+int teco_maxpool2_bf16(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int teco_resize2x_bf16(const void* x, void* y, int32_t N, int32_t h, int32_t w, int32_t C, void* stream);
+/* tf.space_to_depth(x,4) main.py:201 / lib/Teco.py:145-148 and its inverse (gradient). */
+int teco_space_to_depth4_f32(const float* x, float* y, int32_t N, int32_t h, int32_t w, int32_t C,
+                             int32_t out_cpitch, int32_t ch_off, void* stream);
+int teco_depth_to_space4_f32(const float* y, float* x, int32_t N, int32_t h, int32_t w, int32_t C,
+                             int32_t in_cpitch, int32_t ch_off, void* stream);
+/* tf_data_gaussDownby4 lib/ops.py:347-367: 9x9 sigma-1.5 Gaussian, stride 4, VALID, per channel. */
+int teco_gauss_down4_f32(const float* hr, float* lr, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* generic elementwise y = f(a*x + b) with f in TECO_ACT_*; n elements. preprocess/deprocess lib/ops.py:13-22 */
+int teco_affine_act_f32(const float* x, float* y, int64_t n, float a, float b, int32_t act, void* stream);
+/* dx = dy * act'(pre) expressed on the activation OUTPUT y (relu/lrelu/tanh24/sigmoid are invertible enough). */
+int teco_act_bwd_f32(const float* y, const float* dy, float* dx, int64_t n, int32_t act, void* stream);
+/* fp32 <-> bf16 channel-padded copies: dst[n, c_off + c] = src[n, c] for c < C, pixel count npix. */
+int teco_f32_to_bf16_pad(const float* src, void* dst, int64_t npix, int32_t C, int32_t src_cpitch,
+                         int32_t dst_cpitch, int32_t c_off, float scale, float shift, void* stream);
+int teco_bf16_to_f32(const void* src, float* dst, int64_t npix, int32_t C, int32_t src_cpitch, int32_t dst_cpitch,
+                     void* stream);
+/* save_img quantisation lib/ops.py:521-523: clip(x*255,0,255) -> uint8 (truncation), RGB order kept. */
+int teco_to_u8(const float* x, uint8_t* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Batch-norm of the discriminator (lib/ops.py:88-90; lib/Teco.py:38): batch stats, no gamma, eps 1e-3.
+ * stats[0..C) = mean, stats[C..2C) = biased variance (outputs).  lrelu02!=0 fuses LeakyReLU(0.2).
+ * ------------------------------------------------------------------------------------- */
+int teco_bn_train_f32(const float* x, const float* beta, float* y, float* stats, int64_t npix, int32_t C,
+                      float eps, int32_t lrelu02, void* stream);
+int teco_bn_train_bwd_f32(const float* x, const float* y, const float* dy, const float* stats, float* dx,
+                          float* dbeta, int64_t npix, int32_t C, float eps, int32_t lrelu02, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused loss reductions (lib/Teco.py:316-413).  Each writes its scalar (fp32) to out[0] and, when the
+ * gradient pointer is non-NULL, d(loss*gscale)/d(a) elementwise (same shape as a).
+ * ------------------------------------------------------------------------------------- */
+/* mean over pixels of sum_c (a-b)^2 : content loss :320-322, warp loss :329-331 */
+int teco_loss_l2_f32(const float* a, const float* b, float* out, float* da, int64_t npix, int32_t C, float gscale,
+                     void* stream);
+/* mean |a-b| over all elements: ping-pong :364-367; mean over pixels of sum_c|a-b| when per_pixel!=0: layer loss :295-296 */
+int teco_loss_l1_f32(const float* a, const float* b, float* out, float* da, float* db, int64_t npix, int32_t C,
+                     int32_t per_pixel, float gscale, void* stream);
+/* VGG cosine term :346-349 on raw features f,g [npix,C]: 1 - mean_pix( <f,g> / (|f|_eps |g|_eps) ) */
+int teco_loss_cosine_f32(const float* f, const float* g, float* out, float* df, int64_t npix, int32_t C, float gscale,
+                         void* stream);
+/* GAN terms :376,394-399 on sigmoid outputs.  out[0]=mean -log(df+eps)  out[1]=mean -(log(1-df+eps)+log(dr+eps))
+ * out[2]=mean log(dr+eps)  out[3]=mean dr  out[4]=mean df.  Gradients w.r.t. the sigmoid OUTPUTS:
+ * g_adv = d(out0*s_adv)/d df ; g_dis_f, g_dis_r = d(out1*s_dis)/d(df,dr). */
+int teco_loss_gan_f32(const float* d_fake, const float* d_real, float* out, float* g_adv, float* g_dis_f,
+                      float* g_dis_r, int64_t n, float eps, float s_adv, float s_dis, void* stream);
+
+/* tf.train.AdamOptimizer (lib/Teco.py:425,439-440), multi-tensor over one flat buffer of n floats.
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  gscale multiplies g (1/world after allreduce). */
+int teco_adam_f32(float* p, float* m, float* v, const float* g, int64_t n, float lr_t, float b1, float b2, float eps,
+                  float gscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TECO_H_ */

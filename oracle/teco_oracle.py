@@ -249,6 +249,19 @@ def init_generator(seed=1234, num_resblock=16, bias_std=0.0, dtype=torch.float32
     return p
 
 
+def damp_generator(p, gain=0.5):
+    """Scale the residual-block and output-stage weights of a xavier-initialised generator.
+    Why: with untrained xavier weights the RECURRENCE (output -> warp -> input) is expanding -- on the calendar
+    32x32 clip the output std grows x1.5 per frame (0.4 -> 115 after 15 frames) and a 1e-6 input perturbation
+    grows to 2e-2, so no two fp32 implementations can agree.  gain 0.5 gives a contractive, trained-like
+    operating point (output std stays ~0.33, perturbations shrink) where parity over many frames is meaningful."""
+    q = OrderedDict()
+    for k, v in p.items():
+        hit = k.endswith("/weights") and k.startswith("generator/") and ("/resblock_" in k or "/output_stage/" in k)
+        q[k] = v * gain if hit else v
+    return q
+
+
 FNET_LAYERS = [("encoder_1", 6, 32), ("encoder_2", 32, 64), ("encoder_3", 64, 128),
                ("decoder_1", 128, 256), ("decoder_2", 256, 128), ("decoder_3", 128, 64)]
 

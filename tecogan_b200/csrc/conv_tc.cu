@@ -1,0 +1,454 @@
+// bf16 3x3 convolution / 3x3-stride-2 transposed convolution on the 5th-gen tensor cores (sm_100a):
+// TMA halo tile -> shared memory -> tcgen05.mma (kind::f16, fp32 accumulators in TMEM) -> tcgen05.ld
+// epilogue (bias, activation, residual, bf16 store; or fp32 "+bicubic, *2-1" output stage).
+//
+// Replaces, layer by layer, the cuDNN convolutions behind conv2()/conv2_tran() of the reference
+// (lib/ops.py:35-56) as used by generator_F (lib/frvsr.py:44-88) and fnet (lib/frvsr.py:4-41).
+//
+// Implicit GEMM formulation (no im2col buffer, one halo load serves all nine taps):
+//   CTA tile  = 16 image rows x (8*J) pixels; every 16x8 sub-tile is one UMMA with M = 128.
+//   A operand = the halo tile, staged ONCE per Cin block by a 5-D TMA box
+//               (8 ch, 8J+2 px, 18 rows, CB/8 chunks, 1 image) into the UMMA "no-swizzle K-major
+//               canonical" layout [chunk][row][px][8ch]: 8 consecutive pixels x 16 B form a core
+//               matrix, SBO = one halo row, LBO = one channel-chunk plane.  A 3x3 tap (ky,kx) is just a
+//               different descriptor start address (+ky rows, +kx pixels): zero data movement per tap.
+//               TMA out-of-bounds zero fill implements TF 'SAME' padding.
+//   B operand = weights pre-packed on the device as [tap][cin/8][cout][8] bf16 (same canonical layout),
+//               streamed per (Cin block, tap) by 1-D bulk copies through a ring of smem slabs.
+//   D         = fp32 in TMEM, column block (sub-tile, phase) * Cout.
+// Transposed conv (stride 2, TF 'SAME', y[i] = sum_j x[j] w[i-2j]) is the same loop with the nine taps
+// routed to four sub-pixel phase accumulators and a 2x interleaving epilogue.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+#include <cuda.h>
+#include "teco_common.cuh"
+
+namespace {
+
+constexpr int TILE_ROWS = 16;
+constexpr int HALO_ROWS = TILE_ROWS + 2;
+constexpr int MAX_WST = 12;
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+  int N, H, W, Cin, Cout;
+  int tiles_x, tiles_y, J;
+  int mode, act, out_f32_c;
+  float post_scale, post_shift;
+  int CB, nblk, WST;
+  uint32_t halo_stage_bytes, halo_tx_bytes, w_slab_bytes, tmem_cols;
+  const uint8_t* wpk;
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  const float* res_f32;
+  float* out_f32;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// a/b major K (0) @15/@16, N>>3 @17, M>>4 @24.
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int halo_w = 8 * p.J + 2;
+  uint8_t* halo_base = smem;
+  uint8_t* w_base = smem + 2 * p.halo_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)p.WST * p.w_slab_bytes);
+  // bars: [0,2) halo_full, [2,4) halo_empty, [4,4+WST) w_full, [4+MAX_WST, ...) w_empty, then acc_full
+  uint64_t* halo_full = bars;
+  uint64_t* halo_empty = bars + 2;
+  uint64_t* w_full = bars + 4;
+  uint64_t* w_empty = bars + 4 + MAX_WST;
+  uint64_t* acc_full = bars + 4 + 2 * MAX_WST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * MAX_WST + 1);
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x;
+  tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int n = tile / p.tiles_y;
+  const int x0 = tx * 8 * p.J, y0 = ty * TILE_ROWS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&halo_full[i]), 1);
+      mbar_init(smem_u32(&halo_empty[i]), 1);
+    }
+    for (int i = 0; i < p.WST; ++i) {
+      mbar_init(smem_u32(&w_full[i]), 1);
+      mbar_init(smem_u32(&w_empty[i]), 1);
+    }
+    mbar_init(smem_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (one full warp), result lands in smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks_per_blk = p.CB >> 3;
+  const int nacc = p.mode == 1 ? 4 : 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int hs = 0, ws = 0;
+      uint32_t hph = 0, wph = 0;
+      for (int b = 0; b < p.nblk; ++b) {
+        mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
+        mbar_expect_tx(smem_u32(&halo_full[hs]), p.halo_tx_bytes);
+        tma_load_5d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes), &tmap, smem_u32(&halo_full[hs]), 0, x0 - 1,
+                    y0 - 1, b * chunks_per_blk, n);
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
+          mbar_expect_tx(smem_u32(&w_full[ws]), p.w_slab_bytes);
+          const uint8_t* src = p.wpk + ((size_t)(t * (p.Cin >> 3) + b * chunks_per_blk) * p.Cout) * 16;
+          bulk_load_1d(smem_u32(w_base + (size_t)ws * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[ws]));
+          if (++ws == p.WST) { ws = 0; wph ^= 1; }
+        }
+        if (++hs == 2) { hs = 0; hph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc(p.Cout);
+    const uint32_t a_lbo = (uint32_t)(HALO_ROWS * halo_w * 16);
+    const uint32_t a_sbo = (uint32_t)(halo_w * 16);
+    const uint32_t b_lbo = (uint32_t)(p.Cout * 16);
+    const uint32_t b_sbo = 128u;
+    int hs = 0, ws = 0;
+    uint32_t hph = 0, wph = 0;
+    uint32_t started = 0;  // bit (j*nacc+phase): accumulator already written once
+    for (int b = 0; b < p.nblk; ++b) {
+      mbar_wait(smem_u32(&halo_full[hs]), hph);
+      tcgen05_fence_after();
+      const uint32_t halo_addr = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
+      for (int t = 0; t < 9; ++t) {
+        mbar_wait(smem_u32(&w_full[ws]), wph);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const int ky = t / 3, kx = t - 3 * ky;
+          int ry, rx, phase;
+          if (p.mode == 1) {  // transposed conv: tap -> (input offset, output phase)
+            ry = (ky == 2) ? 0 : 1;
+            rx = (kx == 2) ? 0 : 1;
+            phase = ((ky == 1) ? 2 : 0) + ((kx == 1) ? 1 : 0);
+          } else {
+            ry = ky; rx = kx; phase = 0;
+          }
+          const uint32_t w_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
+          for (int j = 0; j < p.J; ++j) {
+            const int acc = j * nacc + phase;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+            for (int s = 0; s < (p.CB >> 4); ++s) {
+              const uint32_t a_addr = halo_addr + (uint32_t)((((2 * s) * HALO_ROWS + ry) * halo_w + rx + 8 * j) * 16);
+              const uint32_t b_addr = w_addr + (uint32_t)((2 * s) * p.Cout * 16);
+              const uint32_t accum = (started >> acc) & 1u;
+              umma_bf16(d_tmem, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, accum);
+              started |= 1u << acc;
+            }
+          }
+          tcgen05_commit(smem_u32(&w_empty[ws]));  // frees the weight slab when these MMAs retire
+        }
+        __syncwarp();
+        if (++ws == p.WST) { ws = 0; wph ^= 1; }
+      }
+      if (lane == 0) tcgen05_commit(smem_u32(&halo_empty[hs]));
+      __syncwarp();
+      if (++hs == 2) { hs = 0; hph ^= 1; }
+    }
+    if (lane == 0) tcgen05_commit(smem_u32(acc_full));
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = 32 * q + lane;       // accumulator row = pixel within the 16x8 sub-tile
+    const int ry = m >> 3, rx = m & 7;
+    mbar_wait(smem_u32(acc_full), 0);
+    tcgen05_fence_after();
+    const int oy_in = y0 + ry;
+    for (int j = 0; j < p.J; ++j) {
+      const int ox_in = x0 + 8 * j + rx;
+      const bool in_img = (oy_in < p.H) && (ox_in < p.W);
+      for (int ph = 0; ph < nacc; ++ph) {
+        int oy, ox, OH, OW;
+        if (p.mode == 1) {
+          oy = 2 * oy_in + (ph >> 1); ox = 2 * ox_in + (ph & 1); OH = 2 * p.H; OW = 2 * p.W;
+        } else {
+          oy = oy_in; ox = ox_in; OH = p.H; OW = p.W;
+        }
+        const size_t pix = ((size_t)n * OH + oy) * OW + ox;
+        const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((j * nacc + ph) * p.Cout);
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          uint32_t r[16];
+          __syncwarp();
+          tmem_ld16(tcol + (uint32_t)c0, r);
+          tmem_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
+            v[i] = teco_act(a, p.act);
+          }
+          if (!in_img) continue;
+          if (p.out_f32) {
+            for (int i = 0; i < 16; ++i) {
+              int c = c0 + i;
+              if (c < p.out_f32_c) {
+                float a = v[i] + (p.res_f32 ? p.res_f32[pix * p.out_f32_c + c] : 0.f);
+                p.out_f32[pix * p.out_f32_c + c] = a * p.post_scale + p.post_shift;
+              }
+            }
+          }
+          if (p.y) {
+            if (p.res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + c0);
+              uint4 r0 = rp[0], r1 = rp[1];
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              o[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.Cout + c0);
+            yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ weight packing
+// out[tap][cin_pad/8][cout_pad][8] bf16 <- w[3,3,cin,cout] (or [3,3,cout,cin] when transpose_layout)
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad, int cout_pad,
+                                    int transpose_layout, const int* __restrict__ cin_perm, __nv_bfloat16* __restrict__ out) {
+  long long total = 9LL * cin_pad * cout_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int e = (int)(i & 7);
+    long long t = i >> 3;
+    int co = (int)(t % cout_pad);
+    t /= cout_pad;
+    int chunk = (int)(t % (cin_pad >> 3));
+    int tap = (int)(t / (cin_pad >> 3));
+    int ci = chunk * 8 + e;
+    int src_ci = cin_perm ? cin_perm[ci] : (ci < cin ? ci : -1);
+    float v = 0.f;
+    if (src_ci >= 0 && src_ci < cin && co < cout)
+      v = transpose_layout ? w[((long long)tap * cout + co) * cin + src_ci] : w[((long long)tap * cin + src_ci) * cout + co];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+extern "C" int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad) {
+  return 9LL * cin_pad * cout_pad * 2;
+}
+
+extern "C" int teco_pack_conv3x3_bf16(const float* w, int32_t cin, int32_t cout, int32_t cin_pad, int32_t cout_pad,
+                                      int32_t transpose_layout, const int32_t* cin_perm, void* wpk, void* stream) {
+  TECO_CHECK_ARG(w && wpk, "teco_pack_conv3x3_bf16: NULL tensor");
+  TECO_CHECK_ARG(cin > 0 && cout > 0 && cin_pad >= cin && cout_pad >= cout && (cin_pad % 16) == 0 && (cout_pad % 16) == 0,
+                 "teco_pack_conv3x3_bf16: padded channels must be multiples of 16 and >= real channels");
+  long long total = 9LL * cin_pad * cout_pad;
+  int blocks = teco_ceil_div(total, 256);
+  if (blocks > 4096) blocks = 4096;
+  pack_conv3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, cin, cout, cin_pad, cout_pad, transpose_layout, cin_perm,
+                                                                (__nv_bfloat16*)wpk);
+  TECO_CUDA_LAUNCH_CHECK("teco_pack_conv3x3_bf16");
+  return TECO_OK;
+}
+
+extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void* wpk, const float* bias, const void* res,
+                               void* y, const float* res_f32, float* out_f32, void* stream) {
+  TECO_CHECK_ARG(d && x && wpk, "teco_conv3x3_tc: NULL argument");
+  TECO_CHECK_ARG(y || out_f32, "teco_conv3x3_tc: no output buffer");
+  TECO_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0, "teco_conv3x3_tc: bad shape N=%d H=%d W=%d", d->N, d->H, d->W);
+  TECO_CHECK_ARG(d->Cin >= 16 && d->Cin % 16 == 0 && d->Cin <= 512, "teco_conv3x3_tc: Cin must be a multiple of 16 in [16,512] (got %d)", d->Cin);
+  TECO_CHECK_ARG(d->Cout >= 16 && d->Cout % 16 == 0 && d->Cout <= 256, "teco_conv3x3_tc: Cout must be a multiple of 16 in [16,256] (got %d)", d->Cout);
+  TECO_CHECK_ARG(d->mode == 0 || d->mode == 1, "teco_conv3x3_tc: unknown mode %d", d->mode);
+  TECO_CHECK_ARG(d->act >= 0 && d->act <= TECO_ACT_SIGMOID, "teco_conv3x3_tc: unknown activation %d", d->act);
+  TECO_CHECK_ARG(!out_f32 || (d->out_f32_c > 0 && d->out_f32_c <= d->Cout), "teco_conv3x3_tc: bad out_f32_c");
+  TECO_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)wpk) & 15) == 0 && (((uintptr_t)y) & 15) == 0 &&
+                     (((uintptr_t)res) & 15) == 0,
+                 "teco_conv3x3_tc: tensors must be 16-byte aligned");
+
+  TcParams p;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.mode = d->mode; p.act = d->act; p.out_f32_c = d->out_f32_c;
+  p.post_scale = d->post_scale; p.post_shift = d->post_shift;
+  p.wpk = (const uint8_t*)wpk; p.bias = bias; p.res = (const __nv_bfloat16*)res; p.y = (__nv_bfloat16*)y;
+  p.res_f32 = res_f32; p.out_f32 = out_f32;
+  p.CB = d->Cin >= 64 ? 64 : d->Cin;
+  TECO_CHECK_ARG(d->Cin % p.CB == 0, "teco_conv3x3_tc: Cin=%d must be <= 64 or a multiple of 64", d->Cin);
+  p.nblk = d->Cin / p.CB;
+  const int nacc = d->mode == 1 ? 4 : 1;
+  const int max_j = 512 / (nacc * d->Cout);
+  TECO_CHECK_ARG(max_j >= 1, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
+  // sub-tiles per CTA: widest tile that still yields >= 2 waves of CTAs, else the narrowest
+  int J = 1;
+  {
+    const int sms = teco_sm_count();
+    const int cand[3] = {4, 2, 1};
+    for (int k = 0; k < 3; ++k) {
+      int j = cand[k];
+      if (j > max_j) continue;
+      long long tiles = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8 * j);
+      if (tiles >= 2LL * sms || j == 1) { J = j; break; }
+    }
+  }
+  p.J = J;
+  p.tiles_x = teco_ceil_div(d->W, 8 * J);
+  p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
+  const int halo_w = 8 * J + 2;
+  p.halo_tx_bytes = (uint32_t)((p.CB / 8) * HALO_ROWS * halo_w * 16);
+  p.halo_stage_bytes = (p.halo_tx_bytes + 127u) & ~127u;
+  p.w_slab_bytes = (uint32_t)(p.CB * d->Cout * 2);
+  const size_t budget = 200 * 1024;
+  int wst = (int)((budget - 2 * (size_t)p.halo_stage_bytes) / p.w_slab_bytes);
+  if (wst > 9 * p.nblk) wst = 9 * p.nblk;
+  if (wst > MAX_WST) wst = MAX_WST;
+  TECO_CHECK_ARG(wst >= 2, "teco_conv3x3_tc: shared memory budget too small (Cin=%d Cout=%d)", d->Cin, d->Cout);
+  p.WST = wst;
+  uint32_t cols = (uint32_t)(J * nacc * d->Cout), tc = 32;
+  while (tc < cols) tc <<= 1;
+  p.tmem_cols = tc;
+  const size_t smem_bytes = 2 * (size_t)p.halo_stage_bytes + (size_t)wst * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8;
+
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    teco_set_error("teco_conv3x3_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return TECO_E_CUDA;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)(d->Cin / 8), (cuuint64_t)d->N};
+  const cuuint64_t gstr[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, 16,
+                              (cuuint64_t)d->H * d->W * d->Cin * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)halo_w, (cuuint32_t)HALO_ROWS, (cuuint32_t)(p.CB / 8), 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    teco_set_error("teco_conv3x3_tc: cuTensorMapEncodeTiled failed with CUresult %d (N=%d H=%d W=%d Cin=%d)", (int)cr, d->N,
+                   d->H, d->W, d->Cin);
+    return TECO_E_CUDA;
+  }
+  static size_t smem_set = 0;
+  if (smem_bytes > smem_set) {
+    TECO_CUDA_CALL(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    smem_set = 220 * 1024;
+  }
+  const long long ctas = (long long)d->N * p.tiles_x * p.tiles_y;
+  conv3x3_tc_kernel<<<(unsigned)ctas, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmap, p);
+  TECO_CUDA_LAUNCH_CHECK("teco_conv3x3_tc");
+  return TECO_OK;
+}

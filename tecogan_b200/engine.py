@@ -1,0 +1,152 @@
+"""Streaming inference recurrence (reference main.py:185-216 graph, main.py:253-268 loop).
+
+State per clip (reference main.py:197-199): pre_inputs (previous LR), pre_gen (previous HR output), pre_warp.
+Per frame i:   i > 0:  flow = fnet(pre_inputs ++ LR_i);  pre_warp = warp(pre_gen, upscale_four(4*pad_sym(flow)))
+               HR_i = generator_F(LR_i ++ space_to_depth(pre_warp));  pre_inputs = LR_i;  pre_gen = deprocess(HR_i)
+frame 0 uses pre_warp = 0.
+
+bf16 mode keeps everything in pre-allocated device buffers and replays ONE CUDA graph per frame
+(~57 tcgen05 launches + warp/s2d + resample kernels); fp32 mode runs the differentiable mirror under no_grad.
+"""
+import torch
+
+from . import config
+from . import kernels as K
+from ._ffi import call, ptr, stream_ptr
+from .tc_nets import (FNetPlan, GeneratorPlan, LR_OFF, S2D_OFF, _ensure_vars_fnet, _ensure_vars_generator,
+                      _f32_slice_to_bf16)
+from .variables import default_store, variable_scope
+
+f32 = torch.float32
+bf16 = torch.bfloat16
+
+
+class InferenceEngine:
+    """B independent clips of LR size h x w streamed frame by frame."""
+
+    def __init__(self, h, w, num_resblock=16, batch=1, use_graph=True, device="cuda"):
+        if h < 8 or w < 8:
+            raise ValueError("InferenceEngine: LR frames must be at least 8x8")
+        self.h, self.w, self.B, self.nrb = h, w, batch, num_resblock
+        self.device = torch.device(device)
+        self.precision = config.precision()
+        self.use_graph = use_graph and self.precision == "bf16"
+        self.lr_in = torch.zeros((batch, h, w, 3), device=self.device, dtype=f32)     # static input buffer
+        self.prev_lr = torch.zeros_like(self.lr_in)
+        self.out01 = torch.zeros((batch, 4 * h, 4 * w, 3), device=self.device, dtype=f32)
+        self.out_u8 = torch.zeros((batch, 4 * h, 4 * w, 3), device=self.device, dtype=torch.uint8)
+        self.frame_idx = 0
+        self.graph = None
+        self.launches_per_frame = 0
+        if self.precision == "bf16":
+            with variable_scope('generator'), variable_scope('generator_unit') as gs:
+                _ensure_vars_generator(num_resblock)
+                self.gen = GeneratorPlan(gs, batch, h, w, num_resblock, self.device)
+            with variable_scope('fnet'), variable_scope('autoencode_unit') as fs:
+                _ensure_vars_fnet()
+                self.fnet = FNetPlan(fs, batch, h, w, self.device)
+            self.launches_per_frame = self.gen.launches + self.fnet.launches + 6
+        else:
+            self.pre_gen = torch.zeros((batch, 4 * h, 4 * w, 3), device=self.device, dtype=f32)
+            self.pre_warp = torch.zeros_like(self.pre_gen)
+
+    # ------------------------------------------------------------------ bf16 / tcgen05 path
+    def _frame_first(self):
+        self.gen.x_in[..., S2D_OFF:S2D_OFF + 48].zero_()
+        _f32_slice_to_bf16(self.lr_in, 0, 3, self.gen.x_in, LR_OFF)
+        self.gen.run(self.lr_in, 3)
+        self._finish()
+
+    def _frame_next(self):
+        g, f = self.gen, self.fnet
+        _f32_slice_to_bf16(self.prev_lr, 0, 3, f.x_in, 0)
+        _f32_slice_to_bf16(self.lr_in, 0, 3, f.x_in, 3)
+        flow_lr = f.run()
+        # fused: symmetric pad + x4 + upscale_four + warp(previous output, read as [-1,1] and deprocessed) + s2d
+        K.warp_s2d_fused(g.out, flow_lr, g.x_in, S2D_OFF, in_scale=0.5, in_shift=0.5)
+        _f32_slice_to_bf16(self.lr_in, 0, 3, g.x_in, LR_OFF)
+        g.run(self.lr_in, 3)
+        self._finish()
+
+    def _finish(self):
+        n = self.out01.numel()
+        call("teco_affine_act_f32", ptr(self.gen.out, f32), ptr(self.out01, f32), n, 0.5, 0.5, 0, stream_ptr())  # deprocess
+        call("teco_to_u8", ptr(self.out01, f32), ptr(self.out_u8, torch.uint8), n, stream_ptr())
+        self.prev_lr.copy_(self.lr_in)
+
+    # ------------------------------------------------------------------ fp32 path (exact-parity mode)
+    def _frame_fp32(self):
+        from .lib.frvsr import fnet, generator_F
+        from .lib.ops import deprocess
+
+        class _F:
+            num_resblock = self.nrb
+        h, w = self.h, self.w
+        with torch.no_grad():
+            cur = self.lr_in
+            if self.frame_idx > 0:
+                with variable_scope('fnet'):
+                    flow_lr = fnet(torch.cat((self.prev_lr, cur), dim=-1), reuse=self.frame_idx > 1)
+                # tf.pad SYMMETRIC + *4 + upscale_four + dense_image_warp + space_to_depth, fused (main.py:212-215,201)
+                s2d = torch.zeros((self.B, h, w, 48), device=self.device, dtype=f32)
+                K.warp_s2d_fused(self.pre_gen, flow_lr, s2d, 0, warped_out=self.pre_warp)
+            else:
+                s2d = torch.zeros((self.B, h, w, 48), device=self.device, dtype=f32)
+            with variable_scope('generator'):
+                gen_out = generator_F(torch.cat((cur, s2d), dim=-1), 3, reuse=self.frame_idx > 0, FLAGS=_F)
+            self.pre_gen = deprocess(gen_out)
+            self.out01.copy_(self.pre_gen)
+            call("teco_to_u8", ptr(self.out01, f32), ptr(self.out_u8, torch.uint8), self.out01.numel(), stream_ptr())
+            self.prev_lr.copy_(cur)
+
+    # ------------------------------------------------------------------ public API
+    def reset(self):
+        self.frame_idx = 0
+
+    def step(self, lr=None):
+        """Advance one frame.  lr: [B,h,w,3] (or [h,w,3] when B == 1) fp32 in [0,1], CUDA or pinned host; if None the
+        caller has already filled self.lr_in.  Returns self.out01 ([B,4h,4w,3] fp32 in [0,1], overwritten each step)."""
+        if lr is not None:
+            if lr.dim() == 3:
+                lr = lr.unsqueeze(0)
+            if tuple(lr.shape) != tuple(self.lr_in.shape):
+                raise ValueError("InferenceEngine.step: expected LR frame of shape %s, got %s"
+                                 % (tuple(self.lr_in.shape), tuple(lr.shape)))
+            self.lr_in.copy_(lr, non_blocking=True)
+        if self.precision != "bf16":
+            self._frame_fp32()
+        elif self.frame_idx == 0:
+            self._frame_first()
+        elif not self.use_graph:
+            self._frame_next()
+        else:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        self.frame_idx += 1
+        return self.out01
+
+    def _capture(self):
+        # warm-up once eagerly on a side stream (sets function attributes, builds tensor maps), then capture
+        snap = (self.gen.out.clone(), self.prev_lr.clone(), self.gen.x_in.clone())
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._frame_next()
+        torch.cuda.current_stream().wait_stream(s)
+        self.gen.out.copy_(snap[0]); self.prev_lr.copy_(snap[1]); self.gen.x_in.copy_(snap[2])
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._frame_next()
+        self.gen.out.copy_(snap[0]); self.prev_lr.copy_(snap[1]); self.gen.x_in.copy_(snap[2])
+
+    def run_sequence(self, frames, out="f32"):
+        """frames: iterable of [h,w,3] / [B,h,w,3] tensors.  Returns a list of CUDA tensors, one per frame
+        ('f32': [0,1] floats; 'u8': save_img quantisation, reference lib/ops.py:521-523)."""
+        self.reset()
+        res = []
+        for fr in frames:
+            self.step(fr)
+            res.append((self.out01 if out == "f32" else self.out_u8).clone())
+        return res

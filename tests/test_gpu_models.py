@@ -1,0 +1,169 @@
+"""GPU parity at network level: the mirror of the reference interface (tecogan_b200/lib) against the golden
+vectors produced by the reference's own code (tests/golden) and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import teco_oracle as O
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+class Flags:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _fresh_store(params):
+    from tecogan_b200 import variables as V
+    st = V.set_default_store(V.VariableStore())
+    st.load(params)
+    return st
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def _psnr(a, b):
+    return O.psnr(a.detach().float().cpu().numpy(), b.detach().float().cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [3, 16])
+def test_generator_fp32_matches_reference_golden(n):
+    from tecogan_b200 import config
+    from tecogan_b200.lib.frvsr import generator_F
+    from tecogan_b200.variables import variable_scope
+    g = _load("generator_n%d" % n)
+    _fresh_store(O.init_generator(seed=int(g["seed"]), num_resblock=n, bias_std=float(g["bias_std"])))
+    config.set_precision("fp32")
+    with torch.no_grad(), variable_scope('generator'):
+        out = generator_F(torch.from_numpy(g["inputs"]).cuda(), 3, reuse=False, FLAGS=Flags(num_resblock=n))
+    err = (out.cpu() - torch.from_numpy(g["out"])).abs().max().item()
+    assert err < 1e-4, err      # fp32 tolerance of SURVEY 8(c)
+
+
+def test_fnet_fp32_matches_reference_golden():
+    from tecogan_b200 import config
+    from tecogan_b200.lib.frvsr import fnet
+    from tecogan_b200.variables import variable_scope
+    g = _load("fnet")
+    _fresh_store(O.init_fnet(seed=int(g["seed"]), bias_std=float(g["bias_std"])))
+    config.set_precision("fp32")
+    with torch.no_grad(), variable_scope('fnet'):
+        out = fnet(torch.from_numpy(g["inputs"]).cuda(), reuse=False)
+    err = (out.cpu() - torch.from_numpy(g["out"])).abs().max().item()
+    assert err < 2e-4, err      # flow is in [-24,24] LR pixels
+
+
+@pytest.mark.parametrize("n,hw", [(3, (12, 10)), (16, (12, 10)), (16, (64, 48))])
+def test_generator_bf16_tensor_core_close_to_oracle(n, hw):
+    from tecogan_b200 import config
+    from tecogan_b200.lib.frvsr import generator_F
+    from tecogan_b200.variables import variable_scope
+    p = O.damp_generator(O.init_generator(seed=12, num_resblock=n, bias_std=0.05))
+    _fresh_store(p)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, hw[0], hw[1], 51, generator=g)
+    ref = O.generator_F(p, x, n)
+    config.set_precision("bf16")
+    with torch.no_grad(), variable_scope('generator'):
+        out = generator_F(x.cuda(), 3, reuse=False, FLAGS=Flags(num_resblock=n))
+    ps = O.psnr(out.cpu().numpy(), ref.numpy(), peak=2.0)
+    assert ps > 45.0, ps        # bf16 tolerance of SURVEY 8(c): PSNR(out, oracle) > 45 dB on the [-1,1] range
+
+
+def test_fnet_bf16_tensor_core_close_to_oracle():
+    from tecogan_b200 import config
+    from tecogan_b200.lib.frvsr import fnet
+    from tecogan_b200.variables import variable_scope
+    p = O.init_fnet(seed=31, bias_std=0.05)
+    _fresh_store(p)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(2, 40, 36, 6, generator=g)
+    ref = O.fnet(p, x)
+    config.set_precision("bf16")
+    with torch.no_grad(), variable_scope('fnet'):
+        out = fnet(x.cuda(), reuse=False)
+    assert tuple(out.shape) == tuple(ref.shape) == (2, 40, 32, 2)
+    err = (out.cpu() - ref).abs()
+    assert err.max().item() < 0.35 and err.mean().item() < 0.03, (err.max().item(), err.mean().item())
+
+
+def _calendar_frames(crop=None, n=10):
+    g = _load("calendar_lr")
+    fr = g["crop32_u8"] if crop else g["full_u8"]
+    fr = fr[:n].astype(np.float32) / 255.0
+    order = O.warmup_order(len(fr))                     # lib/dataloader.py:42-44
+    return [torch.from_numpy(fr[i]) for i in order]
+
+
+def test_config1_calendar_32x32_fp32_engine_matches_oracle():
+    """BASELINE config 1: runGan.py case-1 inference on calendar 32x32x10 (+5 warm-up), N=16, seed 1234."""
+    from tecogan_b200 import config
+    from tecogan_b200.engine import InferenceEngine
+    pg, pf = O.damp_generator(O.init_generator(seed=1234, num_resblock=16)), O.init_fnet(seed=4321)
+    frames = _calendar_frames(crop=True)
+    ref = O.inference_sequence(pg, pf, frames, 16)
+    _fresh_store({**pg, **pf})
+    config.set_precision("fp32")
+    eng = InferenceEngine(32, 32, 16)
+    outs = eng.run_sequence([f.cuda() for f in frames])
+    worst = max((o[0].cpu() - r).abs().max().item() for o, r in zip(outs, ref))
+    assert worst < 1e-4, worst  # after 15 recurrent frames (SURVEY 8c tolerance, on [0,1] outputs)
+
+
+def test_config1_calendar_32x32_bf16_engine_psnr_and_graph_equivalence():
+    from tecogan_b200 import config
+    from tecogan_b200.engine import InferenceEngine
+    pg, pf = O.damp_generator(O.init_generator(seed=1234, num_resblock=16)), O.init_fnet(seed=4321)
+    frames = _calendar_frames(crop=True)
+    ref = O.inference_sequence(pg, pf, frames, 16)
+    _fresh_store({**pg, **pf})
+    config.set_precision("bf16")
+    outs_g = InferenceEngine(32, 32, 16, use_graph=True).run_sequence([f.cuda() for f in frames])
+    outs_e = InferenceEngine(32, 32, 16, use_graph=False).run_sequence([f.cuda() for f in frames])
+    for a, b in zip(outs_g, outs_e):
+        assert torch.equal(a, b)                        # CUDA-graph replay == eager launches, bit for bit
+    ps = [O.psnr(o[0].cpu().numpy(), r.numpy()) for o, r in zip(outs_g[5:], ref[5:])]
+    assert min(ps) > 40.0, ps
+    # Y-PSNR parity with the reference's metric (metrics.py:37-70) against a common stand-in target
+    tgt = [O.save_img_u8(O.bicubic_four(f.unsqueeze(0))[0]) for f in frames[5:]]
+    d = [abs(O.psnr_y(t, O.save_img_u8(o[0].cpu())) - O.psnr_y(t, O.save_img_u8(r))) for t, o, r in zip(tgt, outs_g[5:], ref[5:])]
+    assert max(d) < 0.05, d
+
+
+def test_full_frame_144x180_streaming_exercises_symmetric_pad():
+    """W=180 is not a multiple of 8: fnet sees 144x176 and the flow is SYMMETRIC-padded back (main.py:188-190,212)."""
+    from tecogan_b200 import config
+    from tecogan_b200.engine import InferenceEngine
+    pg, pf = O.init_generator(seed=7, num_resblock=4), O.init_fnet(seed=8)
+    g = _load("calendar_lr")
+    frames = [torch.from_numpy(g["full_u8"][i].astype(np.float32) / 255.0) for i in range(4)]
+    ref = O.inference_sequence(pg, pf, frames, 4)
+    _fresh_store({**pg, **pf})
+    config.set_precision("fp32")
+    outs = InferenceEngine(144, 180, 4).run_sequence([f.cuda() for f in frames])
+    worst = max((o[0].cpu() - r).abs().max().item() for o, r in zip(outs, ref))
+    assert worst < 1e-4, worst
+    config.set_precision("bf16")
+    outs = InferenceEngine(144, 180, 4).run_sequence([f.cuda() for f in frames])
+    ps = [O.psnr(o[0].cpu().numpy(), r.numpy()) for o, r in zip(outs, ref)]
+    assert min(ps) > 40.0, ps
+
+
+def test_batched_clips_are_independent():
+    from tecogan_b200 import config
+    from tecogan_b200.engine import InferenceEngine
+    pg, pf = O.init_generator(seed=1, num_resblock=2), O.init_fnet(seed=2)
+    _fresh_store({**pg, **pf})
+    config.set_precision("bf16")
+    g = torch.Generator().manual_seed(3)
+    clips = torch.rand(2, 3, 32, 48, 3, generator=g).cuda()
+    both = InferenceEngine(32, 48, 2, batch=2).run_sequence([clips[:, t] for t in range(3)])
+    one = InferenceEngine(32, 48, 2, batch=1).run_sequence([clips[1, t] for t in range(3)])
+    for a, b in zip(both, one):
+        assert torch.equal(a[1], b[0])
