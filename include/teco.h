@@ -90,6 +90,11 @@ int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad);
 int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void* wpk, const float* bias,
                     const void* res, void* y, const float* res_f32, float* out_f32, void* stream);
 
+/* Developer hook: when buf != NULL every teco_conv3x3_tc CTA writes clock64() stamps to buf[cta*32 ..] (phase
+ * boundaries: start, setup done, halo landed, first/last weight slab landed, MMAs issued, accumulator ready,
+ * epilogue done, teardown).  buf must hold gridDim*32 int64.  Pass NULL to switch it off. */
+int teco_debug_timing(void* buf);
+
 /* ---------------------------------------------------------------------------------------
  * Warp / resample family (HBM-bound).
  * ------------------------------------------------------------------------------------- */

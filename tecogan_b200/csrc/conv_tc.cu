@@ -36,6 +36,7 @@ struct TcParams {
   int mode, act, out_f32_c;
   float post_scale, post_shift;
   int CB, nblk, WST;
+  int HST, CS, mcast, num_tiles;   // halo stages, cluster size, resident+multicast weights, real tile count
   uint32_t halo_stage_bytes, halo_tx_bytes, w_slab_bytes, tmem_cols;
   const uint8_t* wpk;
   const float* bias;
@@ -43,6 +44,7 @@ struct TcParams {
   __nv_bfloat16* y;
   const float* res_f32;
   float* out_f32;
+  long long* dbg;   // optional [gridDim][16] clock64 stamps (teco_debug_timing)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -66,6 +68,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// Warp-collective wait: one lane polls the mbarrier, the rest park on the warp barrier (keeps 31 lanes per warp
+// from hammering the shared-memory pipe that the TMA engine is writing through).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -78,6 +86,25 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Programmatic dependent launch: let the next kernel in the stream start its prologue now; wait for the
+// previous kernel's results only where they are first needed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -120,7 +147,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
   const int halo_w = 8 * p.J + 2;
   uint8_t* halo_base = smem;
-  uint8_t* w_base = smem + 2 * p.halo_stage_bytes;
+  uint8_t* w_base = smem + (size_t)p.HST * p.halo_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)p.WST * p.w_slab_bytes);
   // bars: [0,2) halo_full, [2,4) halo_empty, [4,4+WST) w_full, [4+MAX_WST, ...) w_empty, then acc_full
   uint64_t* halo_full = bars;
@@ -129,17 +156,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint64_t* w_empty = bars + 4 + MAX_WST;
   uint64_t* acc_full = bars + 4 + 2 * MAX_WST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * MAX_WST + 1);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 + 2 * MAX_WST + 2);   // [Cout]
 
   // tile coordinates
   int tile = blockIdx.x;
+  const bool active = tile < p.num_tiles;    // grid is padded to a multiple of the cluster size
+  if (!active) tile = 0;
   const int tx = tile % p.tiles_x;
   tile /= p.tiles_x;
   const int ty = tile % p.tiles_y;
   const int n = tile / p.tiles_y;
   const int x0 = tx * 8 * p.J, y0 = ty * TILE_ROWS;
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
+#define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  if (threadIdx.x == 0) STAMP(0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < p.HST; ++i) {
       mbar_init(smem_u32(&halo_full[i]), 1);
       mbar_init(smem_u32(&halo_empty[i]), 1);
     }
@@ -158,9 +191,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (p.CS > 1) cluster_sync_all();   // every CTA's mbarriers are initialised before any multicast may signal them
+  else __syncthreads();
   tcgen05_fence_after();
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) STAMP(1);
 
   const int chunks_per_blk = p.CB >> 3;
   const int nacc = p.mode == 1 ? 4 : 1;
@@ -168,24 +204,50 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int hs = 0, ws = 0;
-      uint32_t hph = 0, wph = 0;
-      for (int b = 0; b < p.nblk; ++b) {
-        mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
-        mbar_expect_tx(smem_u32(&halo_full[hs]), p.halo_tx_bytes);
-        tma_load_5d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes), &tmap, smem_u32(&halo_full[hs]), 0, x0 - 1,
-                    y0 - 1, b * chunks_per_blk, n);
-        for (int t = 0; t < 9; ++t) {
-          mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
-          mbar_expect_tx(smem_u32(&w_full[ws]), p.w_slab_bytes);
-          const uint8_t* src = p.wpk + ((size_t)(t * (p.Cin >> 3) + b * chunks_per_blk) * p.Cout) * 16;
-          bulk_load_1d(smem_u32(w_base + (size_t)ws * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[ws]));
-          if (++ws == p.WST) { ws = 0; wph ^= 1; }
+      if (p.mcast) {
+        // Weights do not depend on the previous layer: fetch them before the dependency wait.  Each CTA of the
+        // cluster fetches 1/CS of every slab and multicasts it to all CS CTAs (one L2 read per cluster).
+        const uint32_t crank = p.CS > 1 ? cluster_ctarank() : 0;
+        const uint32_t part = p.w_slab_bytes / (uint32_t)p.CS;
+        const uint16_t mask = (uint16_t)((1u << p.CS) - 1u);
+        for (int sidx = 0; sidx < 9 * p.nblk; ++sidx) {
+          const int b = sidx / 9, t = sidx - 9 * b;
+          mbar_expect_tx(smem_u32(&w_full[sidx]), p.w_slab_bytes);
+          const uint8_t* src = p.wpk + ((size_t)(t * (p.Cin >> 3) + b * chunks_per_blk) * p.Cout) * 16 + (size_t)crank * part;
+          const uint32_t dst = smem_u32(w_base + (size_t)sidx * p.w_slab_bytes) + crank * part;
+          if (p.CS > 1) bulk_load_1d_mcast(dst, src, part, smem_u32(&w_full[sidx]), mask);
+          else bulk_load_1d(dst, src, part, smem_u32(&w_full[sidx]));
         }
-        if (++hs == 2) { hs = 0; hph ^= 1; }
+      }
+      STAMP(9);
+      pdl_wait();   // the previous kernel's output (our input x) is complete and visible from here on
+      STAMP(10);
+      if (active) {
+        int hs = 0, ws = 0;
+        uint32_t hph = 0, wph = 0;
+        for (int b = 0; b < p.nblk; ++b) {
+          mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
+          mbar_expect_tx(smem_u32(&halo_full[hs]), p.halo_tx_bytes);
+          tma_load_5d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes), &tmap, smem_u32(&halo_full[hs]), 0, x0 - 1,
+                      y0 - 1, b * chunks_per_blk, n);
+          if (!p.mcast) {
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
+              mbar_expect_tx(smem_u32(&w_full[ws]), p.w_slab_bytes);
+              const uint8_t* src = p.wpk + ((size_t)(t * (p.Cin >> 3) + b * chunks_per_blk) * p.Cout) * 16;
+              bulk_load_1d(smem_u32(w_base + (size_t)ws * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[ws]));
+              if (++ws == p.WST) { ws = 0; wph ^= 1; }
+            }
+          }
+          if (++hs == p.HST) { hs = 0; hph ^= 1; }
+        }
+      } else if (p.mcast) {
+        // padding CTA of a cluster: it only relays its share of the weights; stay until they have landed here too
+        for (int sidx = 0; sidx < 9 * p.nblk; ++sidx) mbar_wait(smem_u32(&w_full[sidx]), 0);
       }
     }
-  } else if (warp == 1) {
+    __syncwarp();
+  } else if (warp == 1 && active) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = umma_idesc(p.Cout);
     const uint32_t a_lbo = (uint32_t)(HALO_ROWS * halo_w * 16);
@@ -196,12 +258,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     uint32_t hph = 0, wph = 0;
     uint32_t started = 0;  // bit (j*nacc+phase): accumulator already written once
     for (int b = 0; b < p.nblk; ++b) {
-      mbar_wait(smem_u32(&halo_full[hs]), hph);
+      mbar_wait_warp(smem_u32(&halo_full[hs]), hph);
       tcgen05_fence_after();
+      if (lane == 0 && b == 0) STAMP(2);
       const uint32_t halo_addr = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
       for (int t = 0; t < 9; ++t) {
-        mbar_wait(smem_u32(&w_full[ws]), wph);
+        mbar_wait_warp(smem_u32(&w_full[ws]), wph);
         tcgen05_fence_after();
+        if (lane == 0 && b == 0) { if (t == 0 || t == 8) STAMP(t == 0 ? 3 : 4); STAMP(16 + t); }
         if (lane == 0) {
           const int ky = t / 3, kx = t - 3 * ky;
           int ry, rx, phase;
@@ -231,17 +295,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
       if (lane == 0) tcgen05_commit(smem_u32(&halo_empty[hs]));
       __syncwarp();
-      if (++hs == 2) { hs = 0; hph ^= 1; }
+      if (++hs == p.HST) { hs = 0; hph ^= 1; }
     }
     if (lane == 0) tcgen05_commit(smem_u32(acc_full));
+    if (lane == 0) STAMP(5);
     __syncwarp();
-  } else {
+  } else if (warp >= 2 && active) {
     // ===================== epilogue (warps 2..5) =====================
+    for (int c = (int)threadIdx.x - 64; c < p.Cout; c += 128) s_bias[c] = p.bias ? p.bias[c] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    pdl_wait();                                        // res / y belong to the dependency chain
+    if (threadIdx.x == 64) STAMP(25);
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int m = 32 * q + lane;       // accumulator row = pixel within the 16x8 sub-tile
     const int ry = m >> 3, rx = m & 7;
-    mbar_wait(smem_u32(acc_full), 0);
+    const float act_slope = p.act == TECO_ACT_RELU ? 0.f : (p.act == TECO_ACT_LRELU02 ? 0.2f : 1.f);
+    mbar_wait_warp(smem_u32(acc_full), 0);
     tcgen05_fence_after();
+    if (threadIdx.x == 64) STAMP(6);
     const int oy_in = y0 + ry;
     for (int j = 0; j < p.J; ++j) {
       const int ox_in = x0 + 8 * j + rx;
@@ -260,11 +331,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           __syncwarp();
           tmem_ld16(tcol + (uint32_t)c0, r);
           tmem_wait_ld();
+          if (threadIdx.x == 64 && j == 0 && ph == 0 && c0 == 0) STAMP(11);
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
-            v[i] = teco_act(a, p.act);
+            const float a = __uint_as_float(r[i]) + s_bias[c0 + i];
+            v[i] = fmaxf(a, a * act_slope);      // none: slope 1, relu: 0, lrelu: 0.2 -- no per-element branch
+          }
+          if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = teco_act(v[i], p.act);
           }
           if (!in_img) continue;
           if (p.out_f32) {
@@ -298,13 +374,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
             yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
+          if (threadIdx.x == 64 && j == 0 && ph == 0) STAMP(12 + (c0 >> 4 & 3));
         }
       }
     }
   }
 
+  if (threadIdx.x == 64) STAMP(7);
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) STAMP(8);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -349,6 +428,12 @@ PFN_encodeTiled get_encode() {
 
 }  // namespace
 
+static long long* g_dbg_timing = nullptr;
+extern "C" int teco_debug_timing(void* buf) {
+  g_dbg_timing = (long long*)buf;
+  return TECO_OK;
+}
+
 extern "C" int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad) {
   return 9LL * cin_pad * cout_pad * 2;
 }
@@ -386,7 +471,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.mode = d->mode; p.act = d->act; p.out_f32_c = d->out_f32_c;
   p.post_scale = d->post_scale; p.post_shift = d->post_shift;
   p.wpk = (const uint8_t*)wpk; p.bias = bias; p.res = (const __nv_bfloat16*)res; p.y = (__nv_bfloat16*)y;
-  p.res_f32 = res_f32; p.out_f32 = out_f32;
+  p.res_f32 = res_f32; p.out_f32 = out_f32; p.dbg = g_dbg_timing;
   p.CB = d->Cin >= 64 ? 64 : d->Cin;
   TECO_CHECK_ARG(d->Cin % p.CB == 0, "teco_conv3x3_tc: Cin=%d must be <= 64 or a multiple of 64", d->Cin);
   p.nblk = d->Cin / p.CB;
@@ -412,16 +497,22 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.halo_tx_bytes = (uint32_t)((p.CB / 8) * HALO_ROWS * halo_w * 16);
   p.halo_stage_bytes = (p.halo_tx_bytes + 127u) & ~127u;
   p.w_slab_bytes = (uint32_t)(p.CB * d->Cout * 2);
+  p.HST = p.nblk > 1 ? 2 : 1;
   const size_t budget = 200 * 1024;
-  int wst = (int)((budget - 2 * (size_t)p.halo_stage_bytes) / p.w_slab_bytes);
+  int wst = (int)((budget - (size_t)p.HST * p.halo_stage_bytes) / p.w_slab_bytes);
   if (wst > 9 * p.nblk) wst = 9 * p.nblk;
   if (wst > MAX_WST) wst = MAX_WST;
   TECO_CHECK_ARG(wst >= 2, "teco_conv3x3_tc: shared memory budget too small (Cin=%d Cout=%d)", d->Cin, d->Cout);
   p.WST = wst;
+  // all weight slabs resident -> load them once, before the dependency wait, multicast across a 4-CTA cluster
+  p.mcast = (wst == 9 * p.nblk) ? 1 : 0;
+  p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
+  p.CS = (p.mcast && p.num_tiles >= 8 && (p.w_slab_bytes % (4 * 16)) == 0) ? 4 : 1;
   uint32_t cols = (uint32_t)(J * nacc * d->Cout), tc = 32;
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
-  const size_t smem_bytes = 2 * (size_t)p.halo_stage_bytes + (size_t)wst * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8;
+  const size_t smem_bytes = (size_t)p.HST * p.halo_stage_bytes + (size_t)wst * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 +
+                            256 * sizeof(float);
 
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -447,8 +538,31 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     TECO_CUDA_CALL(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     smem_set = 220 * 1024;
   }
-  const long long ctas = (long long)d->N * p.tiles_x * p.tiles_y;
-  conv3x3_tc_kernel<<<(unsigned)ctas, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmap, p);
+  const unsigned ctas = (unsigned)((p.num_tiles + p.CS - 1) / p.CS * p.CS);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+  attrs[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (p.CS > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = (unsigned)p.CS;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, tmap, p);
+  if (le != cudaSuccess) {
+    teco_set_error("teco_conv3x3_tc: launch failed: %s (grid %u, cluster %d, smem %zu)", cudaGetErrorString(le), ctas, p.CS, smem_bytes);
+    return TECO_E_CUDA;
+  }
   TECO_CUDA_LAUNCH_CHECK("teco_conv3x3_tc");
   return TECO_OK;
 }
