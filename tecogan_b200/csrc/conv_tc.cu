@@ -1,23 +1,27 @@
 // bf16 3x3 convolution / 3x3-stride-2 transposed convolution on the 5th-gen tensor cores (sm_100a):
-// TMA halo tile -> shared memory -> tcgen05.mma (kind::f16, fp32 accumulators in TMEM) -> tcgen05.ld
+// TMA halo tiles -> shared memory -> tcgen05.mma (kind::f16, fp32 accumulators in TMEM) -> tcgen05.ld
 // epilogue (bias, activation, residual, bf16 store; or fp32 "+bicubic, *2-1" output stage).
 //
 // Replaces, layer by layer, the cuDNN convolutions behind conv2()/conv2_tran() of the reference
 // (lib/ops.py:35-56) as used by generator_F (lib/frvsr.py:44-88) and fnet (lib/frvsr.py:4-41).
 //
-// Implicit GEMM formulation (no im2col buffer, one halo load serves all nine taps):
-//   CTA tile  = 16 image rows x (8*J) pixels; every 16x8 sub-tile is one UMMA with M = 128.
-//   A operand = the halo tile, staged ONCE per Cin block by a 5-D TMA box
-//               (8 ch, 8J+2 px, 18 rows, CB/8 chunks, 1 image) into the UMMA "no-swizzle K-major
-//               canonical" layout [chunk][row][px][8ch]: 8 consecutive pixels x 16 B form a core
-//               matrix, SBO = one halo row, LBO = one channel-chunk plane.  A 3x3 tap (ky,kx) is just a
-//               different descriptor start address (+ky rows, +kx pixels): zero data movement per tap.
+// Implicit GEMM, no im2col buffer:
+//   CTA tile  = 16 image rows x (8*J) pixels; every 16x8 sub-tile is one UMMA accumulator with M = 128.
+//   A operand = NHWC bf16 activations, 64 channels = one 128-byte row per pixel.  Per 64-channel block the halo is
+//               staged by THREE 4-D TMA boxes (64 ch, 8J px, 18 rows, 1 image), one per horizontal tap offset kx,
+//               with SWIZZLE_128B.  Each box is the UMMA canonical K-major SW128 layout as it lands
+//               (8 consecutive pixels = one 1024-byte swizzle atom, SBO = one box row).  Vertical taps ky are
+//               descriptor start-address offsets of whole box rows (atom aligned), so 3 loads serve 9 taps.
 //               TMA out-of-bounds zero fill implements TF 'SAME' padding.
-//   B operand = weights pre-packed on the device as [tap][cin/8][cout][8] bf16 (same canonical layout),
-//               streamed per (Cin block, tap) by 1-D bulk copies through a ring of smem slabs.
+//   B operand = weights pre-packed on the device as [cin/64][tap][cout][64 cin] bf16 in the same SW128 image,
+//               streamed by 1-D bulk copies.  When a whole layer fits (64->64: 72 KB) the slabs are fetched once,
+//               BEFORE the programmatic-dependent-launch wait, and multicast across a 4-CTA cluster.
 //   D         = fp32 in TMEM, column block (sub-tile, phase) * Cout.
-// Transposed conv (stride 2, TF 'SAME', y[i] = sum_j x[j] w[i-2j]) is the same loop with the nine taps
-// routed to four sub-pixel phase accumulators and a 2x interleaving epilogue.
+// Transposed conv (stride 2, TF 'SAME', y[i] = sum_j x[j] w[i-2j]) is the same loop with the nine taps routed to
+// four sub-pixel phase accumulators and a 2x interleaving epilogue.
+//
+// Why SW128 and not the no-swizzle layout (round-1 measurement, profiles/conv_tc_r01_notes.md): with 16-byte core
+// matrix rows every tcgen05.mma took ~250 cycles instead of ~32-48, and the 16-byte TMA rows ran at ~10 B/clk/SM.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
 #include <cuda.h>
@@ -27,6 +31,7 @@ namespace {
 
 constexpr int TILE_ROWS = 16;
 constexpr int HALO_ROWS = TILE_ROWS + 2;
+constexpr int CB = 64;                 // channels per K block = one 128-byte swizzled row
 constexpr int MAX_WST = 12;
 constexpr int NUM_THREADS = 192;
 
@@ -35,16 +40,16 @@ struct TcParams {
   int tiles_x, tiles_y, J;
   int mode, act, out_f32_c;
   float post_scale, post_shift;
-  int CB, nblk, WST;
-  int HST, CS, mcast, num_tiles;   // halo stages, cluster size, resident+multicast weights, real tile count
-  uint32_t halo_stage_bytes, halo_tx_bytes, w_slab_bytes, tmem_cols;
+  int nblk, WST, TPS, KS;              // Cin/64, weight ring stages, taps per weight slab (1 or 3), K-split chains
+  int HST, CS, mcast, num_tiles;       // halo stages, cluster size, resident+multicast weights, real tile count
+  uint32_t copy_bytes, halo_stage_bytes, w_slab_bytes, tmem_cols;
   const uint8_t* wpk;
   const float* bias;
   const __nv_bfloat16* res;
   __nv_bfloat16* y;
   const float* res_f32;
   float* out_f32;
-  long long* dbg;   // optional [gridDim][16] clock64 stamps (teco_debug_timing)
+  long long* dbg;                      // optional [gridDim][32] clock64 stamps (teco_debug_timing)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -74,11 +79,11 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
   __syncwarp();
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -118,6 +123,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One elected lane of a fully converged warp (elect.sync): keeps the surrounding address arithmetic warp-uniform so
+// ptxas holds the UMMA descriptors in uniform registers instead of a per-MMA R2UR waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -127,11 +139,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=0.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+// UMMA shared-memory descriptor, K-major SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4 (=1, unused for swizzled K-major), [32,46) SBO>>4, [46,48) version=1,
+// [61,64) layout type = 2 (SWIZZLE_128B).  Canonical layout ((8,n),2):((8,SBO),1) in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) |
+         (2ull << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
 // a/b major K (0) @15/@16, N>>3 @17, M>>4 @24.
@@ -140,16 +153,19 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 }
 
 // ------------------------------------------------------------------ the kernel
+// MODE 0 conv / 1 transposed conv; TPS taps per weight slab; J sub-tiles per CTA; KS K-split accumulator chains.
+// They are compile-time so that the MMA issue loop is a fully unrolled stream of UTCHMMA whose descriptors differ
+// from per-stage bases by immediates (uniform-datapath adds, no per-instruction R2UR).
+template <int MODE, int TPS, int J, int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int halo_w = 8 * p.J + 2;
-  uint8_t* halo_base = smem;
-  uint8_t* w_base = smem + (size_t)p.HST * p.halo_stage_bytes;
+  uint8_t* halo_base = smem;                                             // HST stages x 3 kx-copies
+  uint8_t* w_base = smem + (size_t)p.HST * p.halo_stage_bytes;           // WST weight slabs
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)p.WST * p.w_slab_bytes);
-  // bars: [0,2) halo_full, [2,4) halo_empty, [4,4+WST) w_full, [4+MAX_WST, ...) w_empty, then acc_full
   uint64_t* halo_full = bars;
   uint64_t* halo_empty = bars + 2;
   uint64_t* w_full = bars + 4;
@@ -166,7 +182,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   tile /= p.tiles_x;
   const int ty = tile % p.tiles_y;
   const int n = tile / p.tiles_y;
-  const int x0 = tx * 8 * p.J, y0 = ty * TILE_ROWS;
+  const int x0 = tx * 8 * J, y0 = ty * TILE_ROWS;
   long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
 #define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 0) STAMP(0);
@@ -198,8 +214,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) STAMP(1);
 
-  const int chunks_per_blk = p.CB >> 3;
-  const int nacc = p.mode == 1 ? 4 : 1;
+  constexpr int nacc = MODE == 1 ? 4 : 1;
+  constexpr int ncopies = MODE == 1 ? 2 : 3;     // horizontal tap offsets that occur (tconv only reads x-1, x)
+  constexpr int slabs_per_blk = 9 / TPS;
+  constexpr int row_bytes = 8 * J * 128;         // one box row (8J pixels x 128 B)
+  constexpr uint32_t copy_bytes = (uint32_t)(HALO_ROWS * row_bytes);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -210,10 +229,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const uint32_t crank = p.CS > 1 ? cluster_ctarank() : 0;
         const uint32_t part = p.w_slab_bytes / (uint32_t)p.CS;
         const uint16_t mask = (uint16_t)((1u << p.CS) - 1u);
-        for (int sidx = 0; sidx < 9 * p.nblk; ++sidx) {
-          const int b = sidx / 9, t = sidx - 9 * b;
+        for (int sidx = 0; sidx < slabs_per_blk * p.nblk; ++sidx) {
+          const int b = sidx / slabs_per_blk, g = sidx - slabs_per_blk * b;
           mbar_expect_tx(smem_u32(&w_full[sidx]), p.w_slab_bytes);
-          const uint8_t* src = p.wpk + ((size_t)(t * (p.Cin >> 3) + b * chunks_per_blk) * p.Cout) * 16 + (size_t)crank * part;
+          // global layout [blk][tap][cout][64]: a slab = TPS consecutive taps of one block
+          const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout) * 128 + (size_t)crank * part;
           const uint32_t dst = smem_u32(w_base + (size_t)sidx * p.w_slab_bytes) + crank * part;
           if (p.CS > 1) bulk_load_1d_mcast(dst, src, part, smem_u32(&w_full[sidx]), mask);
           else bulk_load_1d(dst, src, part, smem_u32(&w_full[sidx]));
@@ -227,14 +247,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         uint32_t hph = 0, wph = 0;
         for (int b = 0; b < p.nblk; ++b) {
           mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
-          mbar_expect_tx(smem_u32(&halo_full[hs]), p.halo_tx_bytes);
-          tma_load_5d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes), &tmap, smem_u32(&halo_full[hs]), 0, x0 - 1,
-                      y0 - 1, b * chunks_per_blk, n);
+          mbar_expect_tx(smem_u32(&halo_full[hs]), copy_bytes * ncopies);
+          for (int c = 0; c < ncopies; ++c)
+            tma_load_4d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes + (size_t)c * copy_bytes), &tmap,
+                        smem_u32(&halo_full[hs]), b * CB, x0 - 1 + c, y0 - 1, n);
           if (!p.mcast) {
-            for (int t = 0; t < 9; ++t) {
+            for (int g = 0; g < slabs_per_blk; ++g) {
               mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
               mbar_expect_tx(smem_u32(&w_full[ws]), p.w_slab_bytes);
-              const uint8_t* src = p.wpk + ((size_t)(t * (p.Cin >> 3) + b * chunks_per_blk) * p.Cout) * 16;
+              const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout) * 128;
               bulk_load_1d(smem_u32(w_base + (size_t)ws * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[ws]));
               if (++ws == p.WST) { ws = 0; wph ^= 1; }
             }
@@ -243,17 +264,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
       } else if (p.mcast) {
         // padding CTA of a cluster: it only relays its share of the weights; stay until they have landed here too
-        for (int sidx = 0; sidx < 9 * p.nblk; ++sidx) mbar_wait(smem_u32(&w_full[sidx]), 0);
+        for (int sidx = 0; sidx < slabs_per_blk * p.nblk; ++sidx) mbar_wait(smem_u32(&w_full[sidx]), 0);
       }
     }
     __syncwarp();
   } else if (warp == 1 && active) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = umma_idesc(p.Cout);
-    const uint32_t a_lbo = (uint32_t)(HALO_ROWS * halo_w * 16);
-    const uint32_t a_sbo = (uint32_t)(halo_w * 16);
-    const uint32_t b_lbo = (uint32_t)(p.Cout * 16);
-    const uint32_t b_sbo = 128u;
+    constexpr uint32_t a_sbo = (uint32_t)row_bytes;   // next 8-pixel group of the M=128 sub-tile = next image row
+    constexpr uint32_t b_sbo = 1024u;                 // next 8 output channels
     int hs = 0, ws = 0;
     uint32_t hph = 0, wph = 0;
     uint32_t started = 0;  // bit (j*nacc+phase): accumulator already written once
@@ -262,42 +281,70 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       tcgen05_fence_after();
       if (lane == 0 && b == 0) STAMP(2);
       const uint32_t halo_addr = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
-      for (int t = 0; t < 9; ++t) {
+      for (int g = 0; g < slabs_per_blk; ++g) {
         mbar_wait_warp(smem_u32(&w_full[ws]), wph);
         tcgen05_fence_after();
-        if (lane == 0 && b == 0) { if (t == 0 || t == 8) STAMP(t == 0 ? 3 : 4); STAMP(16 + t); }
-        if (lane == 0) {
-          const int ky = t / 3, kx = t - 3 * ky;
-          int ry, rx, phase;
-          if (p.mode == 1) {  // transposed conv: tap -> (input offset, output phase)
-            ry = (ky == 2) ? 0 : 1;
-            rx = (kx == 2) ? 0 : 1;
-            phase = ((ky == 1) ? 2 : 0) + ((kx == 1) ? 1 : 0);
-          } else {
-            ry = ky; rx = kx; phase = 0;
+        if (lane == 0 && b == 0) STAMP(16 + g);
+        {
+          // Whole (converged) warp computes the warp-uniform bases; one elected lane issues the unrolled MMA stream.
+          const uint32_t slab_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
+          const uint64_t a_base = umma_desc_sw128(halo_addr, a_sbo);
+          const uint64_t b_base = umma_desc_sw128(slab_addr, b_sbo);
+          const uint32_t tap_stride16 = (uint32_t)(p.Cout * 128) >> 4;   // weight bytes per tap, in descriptor units
+          // per-tap row/copy/phase (TPS == 3: ky = g, kx = tt; TPS == 1: tap = g)
+          uint32_t a_off16[TPS], acc_idx[TPS];
+#pragma unroll
+          for (int tt = 0; tt < TPS; ++tt) {
+            const int t = g * TPS + tt;
+            const int ky = (TPS == 3) ? g : t / 3, kx = (TPS == 3) ? tt : t - 3 * (t / 3);
+            int ry, rx, phase;
+            if (MODE == 1) {  // transposed conv: tap -> (input offset, output phase)
+              ry = (ky == 2) ? 0 : 1;
+              rx = (kx == 2) ? 0 : 1;
+              phase = ((ky == 1) ? 2 : 0) + ((kx == 1) ? 1 : 0);
+            } else {
+              ry = ky; rx = kx; phase = 0;
+            }
+            a_off16[tt] = ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
+            acc_idx[tt] = (uint32_t)(phase * KS + (KS > 1 ? tt : 0));
           }
-          const uint32_t w_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
-          for (int j = 0; j < p.J; ++j) {
-            const int acc = j * nacc + phase;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
-            for (int s = 0; s < (p.CB >> 4); ++s) {
-              const uint32_t a_addr = halo_addr + (uint32_t)((((2 * s) * HALO_ROWS + ry) * halo_w + rx + 8 * j) * 16);
-              const uint32_t b_addr = w_addr + (uint32_t)((2 * s) * p.Cout * 16);
-              const uint32_t accum = (started >> acc) & 1u;
-              umma_bf16(d_tmem, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, accum);
-              started |= 1u << acc;
+          const uint32_t started_now = started;
+          if (elect_one()) {
+            // order: sub-tile, k-step, tap -> consecutive MMAs hit different accumulators when KS > 1 / MODE == 1
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+#pragma unroll
+              for (int s = 0; s < CB / 16; ++s) {
+#pragma unroll
+                for (int tt = 0; tt < TPS; ++tt) {
+                  const uint32_t acc = (uint32_t)(j * nacc * KS) + acc_idx[tt];
+                  uint32_t accum = 1u;
+                  if (s == 0) {   // first k-step of this slab: overwrite only if nobody has written this accumulator yet
+                    accum = (started_now >> acc) & 1u;
+#pragma unroll
+                    for (int t2 = 0; t2 < tt; ++t2) accum |= (acc_idx[t2] == acc_idx[tt]) ? 1u : 0u;
+                  }
+                  umma_bf16(tmem_base + acc * (uint32_t)p.Cout, a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
+                            b_base + tt * tap_stride16 + (uint32_t)((s * 32) >> 4), idesc, accum);
+                }
+              }
             }
           }
-          tcgen05_commit(smem_u32(&w_empty[ws]));  // frees the weight slab when these MMAs retire
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int tt = 0; tt < TPS; ++tt) started |= 1u << ((uint32_t)(j * nacc * KS) + acc_idx[tt]);
+          if (elect_one()) tcgen05_commit(smem_u32(&w_empty[ws]));  // frees the weight slab when these MMAs retire
         }
         __syncwarp();
         if (++ws == p.WST) { ws = 0; wph ^= 1; }
       }
-      if (lane == 0) tcgen05_commit(smem_u32(&halo_empty[hs]));
+      if (elect_one()) tcgen05_commit(smem_u32(&halo_empty[hs]));
       __syncwarp();
       if (++hs == p.HST) { hs = 0; hph ^= 1; }
     }
-    if (lane == 0) tcgen05_commit(smem_u32(acc_full));
+    if (elect_one()) tcgen05_commit(smem_u32(acc_full));
     if (lane == 0) STAMP(5);
     __syncwarp();
   } else if (warp >= 2 && active) {
@@ -314,23 +361,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     tcgen05_fence_after();
     if (threadIdx.x == 64) STAMP(6);
     const int oy_in = y0 + ry;
-    for (int j = 0; j < p.J; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int ox_in = x0 + 8 * j + rx;
       const bool in_img = (oy_in < p.H) && (ox_in < p.W);
       for (int ph = 0; ph < nacc; ++ph) {
         int oy, ox, OH, OW;
-        if (p.mode == 1) {
+        if (MODE == 1) {
           oy = 2 * oy_in + (ph >> 1); ox = 2 * ox_in + (ph & 1); OH = 2 * p.H; OW = 2 * p.W;
         } else {
           oy = oy_in; ox = ox_in; OH = p.H; OW = p.W;
         }
         const size_t pix = ((size_t)n * OH + oy) * OW + ox;
-        const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((j * nacc + ph) * p.Cout);
+        const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((j * nacc + ph) * KS * p.Cout);
         for (int c0 = 0; c0 < p.Cout; c0 += 16) {
           uint32_t r[16];
           __syncwarp();
           tmem_ld16(tcol + (uint32_t)c0, r);
-          tmem_wait_ld();
+          if (KS == 3) {   // K-split chains: issue all three TMEM loads, wait once, add
+            uint32_t r2[16], r3[16];
+            tmem_ld16(tcol + (uint32_t)(p.Cout + c0), r2);
+            tmem_ld16(tcol + (uint32_t)(2 * p.Cout + c0), r3);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]) + __uint_as_float(r3[i]));
+          } else {
+            tmem_wait_ld();
+          }
           if (threadIdx.x == 64 && j == 0 && ph == 0 && c0 == 0) STAMP(11);
           float v[16];
 #pragma unroll
@@ -390,18 +447,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 }
 
 // ------------------------------------------------------------------ weight packing
-// out[tap][cin_pad/8][cout_pad][8] bf16 <- w[3,3,cin,cout] (or [3,3,cout,cin] when transpose_layout)
+// out[blk][tap][cout_pad][64] bf16 in the SWIZZLE_128B image (16-byte chunk j of row r stored at chunk j ^ (r & 7))
+//   <- w[3,3,cin,cout] (or [3,3,cout,cin] when transpose_layout); packed input channel k reads cin_perm[k] (-1 = zero).
 __global__ void pack_conv3x3_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad, int cout_pad,
                                     int transpose_layout, const int* __restrict__ cin_perm, __nv_bfloat16* __restrict__ out) {
   long long total = 9LL * cin_pad * cout_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int e = (int)(i & 7);
-    long long t = i >> 3;
+    int jpos = (int)((i >> 3) & 7);
+    long long t = i >> 6;
     int co = (int)(t % cout_pad);
     t /= cout_pad;
-    int chunk = (int)(t % (cin_pad >> 3));
-    int tap = (int)(t / (cin_pad >> 3));
-    int ci = chunk * 8 + e;
+    int tap = (int)(t % 9);
+    int blk = (int)(t / 9);
+    int j = jpos ^ (co & 7);
+    int ci = blk * 64 + j * 8 + e;
     int src_ci = cin_perm ? cin_perm[ci] : (ci < cin ? ci : -1);
     float v = 0.f;
     if (src_ci >= 0 && src_ci < cin && co < cout)
@@ -426,9 +486,10 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
+long long* g_dbg_timing = nullptr;
+
 }  // namespace
 
-static long long* g_dbg_timing = nullptr;
 extern "C" int teco_debug_timing(void* buf) {
   g_dbg_timing = (long long*)buf;
   return TECO_OK;
@@ -441,8 +502,8 @@ extern "C" int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad) {
 extern "C" int teco_pack_conv3x3_bf16(const float* w, int32_t cin, int32_t cout, int32_t cin_pad, int32_t cout_pad,
                                       int32_t transpose_layout, const int32_t* cin_perm, void* wpk, void* stream) {
   TECO_CHECK_ARG(w && wpk, "teco_pack_conv3x3_bf16: NULL tensor");
-  TECO_CHECK_ARG(cin > 0 && cout > 0 && cin_pad >= cin && cout_pad >= cout && (cin_pad % 16) == 0 && (cout_pad % 16) == 0,
-                 "teco_pack_conv3x3_bf16: padded channels must be multiples of 16 and >= real channels");
+  TECO_CHECK_ARG(cin > 0 && cout > 0 && cin_pad >= cin && cout_pad >= cout && (cin_pad % 64) == 0 && (cout_pad % 16) == 0,
+                 "teco_pack_conv3x3_bf16: cin_pad must be a multiple of 64 and cout_pad a multiple of 16, both >= the real channels");
   long long total = 9LL * cin_pad * cout_pad;
   int blocks = teco_ceil_div(total, 256);
   if (blocks > 4096) blocks = 4096;
@@ -457,7 +518,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   TECO_CHECK_ARG(d && x && wpk, "teco_conv3x3_tc: NULL argument");
   TECO_CHECK_ARG(y || out_f32, "teco_conv3x3_tc: no output buffer");
   TECO_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0, "teco_conv3x3_tc: bad shape N=%d H=%d W=%d", d->N, d->H, d->W);
-  TECO_CHECK_ARG(d->Cin >= 16 && d->Cin % 16 == 0 && d->Cin <= 512, "teco_conv3x3_tc: Cin must be a multiple of 16 in [16,512] (got %d)", d->Cin);
+  TECO_CHECK_ARG(d->Cin >= 64 && d->Cin % 64 == 0 && d->Cin <= 512, "teco_conv3x3_tc: Cin must be a multiple of 64 in [64,512] (got %d)", d->Cin);
   TECO_CHECK_ARG(d->Cout >= 16 && d->Cout % 16 == 0 && d->Cout <= 256, "teco_conv3x3_tc: Cout must be a multiple of 16 in [16,256] (got %d)", d->Cout);
   TECO_CHECK_ARG(d->mode == 0 || d->mode == 1, "teco_conv3x3_tc: unknown mode %d", d->mode);
   TECO_CHECK_ARG(d->act >= 0 && d->act <= TECO_ACT_SIGMOID, "teco_conv3x3_tc: unknown activation %d", d->act);
@@ -472,47 +533,47 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.post_scale = d->post_scale; p.post_shift = d->post_shift;
   p.wpk = (const uint8_t*)wpk; p.bias = bias; p.res = (const __nv_bfloat16*)res; p.y = (__nv_bfloat16*)y;
   p.res_f32 = res_f32; p.out_f32 = out_f32; p.dbg = g_dbg_timing;
-  p.CB = d->Cin >= 64 ? 64 : d->Cin;
-  TECO_CHECK_ARG(d->Cin % p.CB == 0, "teco_conv3x3_tc: Cin=%d must be <= 64 or a multiple of 64", d->Cin);
-  p.nblk = d->Cin / p.CB;
+  p.nblk = d->Cin / CB;
+  p.HST = p.nblk > 1 ? 2 : 1;
   const int nacc = d->mode == 1 ? 4 : 1;
-  const int max_j = 512 / (nacc * d->Cout);
-  TECO_CHECK_ARG(max_j >= 1, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
-  // sub-tiles per CTA: widest tile that still yields >= 2 waves of CTAs, else the narrowest
+  const size_t budget = 208 * 1024;
+  const int sms = teco_sm_count();
+  // sub-tiles per CTA: prefer the wider tile when it still yields >= 2 waves of CTAs and fits TMEM / smem
   int J = 1;
-  {
-    const int sms = teco_sm_count();
-    const int cand[3] = {4, 2, 1};
-    for (int k = 0; k < 3; ++k) {
-      int j = cand[k];
-      if (j > max_j) continue;
-      long long tiles = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8 * j);
-      if (tiles >= 2LL * sms || j == 1) { J = j; break; }
-    }
+  for (int j = 2; j >= 1; --j) {
+    if (j * nacc * d->Cout > 512) continue;
+    size_t a_bytes = (size_t)p.HST * 3 * HALO_ROWS * 8 * j * 128;
+    if (a_bytes + 2 * (size_t)d->Cout * 128 > budget) continue;
+    long long tiles = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8 * j);
+    if (tiles >= 2LL * sms || j == 1) { J = j; break; }
   }
+  TECO_CHECK_ARG(J * nacc * d->Cout <= 512, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
   p.J = J;
   p.tiles_x = teco_ceil_div(d->W, 8 * J);
   p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
-  const int halo_w = 8 * J + 2;
-  p.halo_tx_bytes = (uint32_t)((p.CB / 8) * HALO_ROWS * halo_w * 16);
-  p.halo_stage_bytes = (p.halo_tx_bytes + 127u) & ~127u;
-  p.w_slab_bytes = (uint32_t)(p.CB * d->Cout * 2);
-  p.HST = p.nblk > 1 ? 2 : 1;
-  const size_t budget = 200 * 1024;
-  int wst = (int)((budget - (size_t)p.HST * p.halo_stage_bytes) / p.w_slab_bytes);
-  if (wst > 9 * p.nblk) wst = 9 * p.nblk;
-  if (wst > MAX_WST) wst = MAX_WST;
-  TECO_CHECK_ARG(wst >= 2, "teco_conv3x3_tc: shared memory budget too small (Cin=%d Cout=%d)", d->Cin, d->Cout);
-  p.WST = wst;
-  // all weight slabs resident -> load them once, before the dependency wait, multicast across a 4-CTA cluster
-  p.mcast = (wst == 9 * p.nblk) ? 1 : 0;
+  p.copy_bytes = (uint32_t)(HALO_ROWS * 8 * J * 128);
+  p.halo_stage_bytes = 3 * p.copy_bytes;
+  const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
+  const size_t tap_bytes = (size_t)d->Cout * 128;
+  // whole layer resident?  then 3 taps per slab (3 barriers per block), fetched once, multicast over a 4-CTA cluster
   p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
-  p.CS = (p.mcast && p.num_tiles >= 8 && (p.w_slab_bytes % (4 * 16)) == 0) ? 4 : 1;
-  uint32_t cols = (uint32_t)(J * nacc * d->Cout), tc = 32;
+  if (a_total + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
+    p.mcast = 1; p.TPS = 3; p.WST = 3 * p.nblk;
+  } else {
+    p.mcast = 0; p.TPS = 1;
+    int wst = (int)((budget - a_total) / tap_bytes);
+    if (wst > 9 * p.nblk) wst = 9 * p.nblk;
+    if (wst > MAX_WST) wst = MAX_WST;
+    TECO_CHECK_ARG(wst >= 2, "teco_conv3x3_tc: shared memory budget too small (Cin=%d Cout=%d)", d->Cin, d->Cout);
+    p.WST = wst;
+  }
+  p.w_slab_bytes = (uint32_t)(p.TPS * tap_bytes);
+  p.KS = (p.TPS == 3 && d->mode == 0 && J * 3 * d->Cout <= 512) ? 3 : 1;
+  p.CS = (p.mcast && p.num_tiles >= 8) ? 4 : 1;
+  uint32_t cols = (uint32_t)(J * nacc * p.KS * d->Cout), tc = 32;
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
-  const size_t smem_bytes = (size_t)p.HST * p.halo_stage_bytes + (size_t)wst * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 +
-                            256 * sizeof(float);
+  const size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float);
 
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -520,24 +581,29 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     return TECO_E_CUDA;
   }
   CUtensorMap tmap;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)(d->Cin / 8), (cuuint64_t)d->N};
-  const cuuint64_t gstr[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, 16,
-                              (cuuint64_t)d->H * d->W * d->Cin * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)halo_w, (cuuint32_t)HALO_ROWS, (cuuint32_t)(p.CB / 8), 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+  const cuuint64_t gstr[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(8 * J), (cuuint32_t)HALO_ROWS, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     teco_set_error("teco_conv3x3_tc: cuTensorMapEncodeTiled failed with CUresult %d (N=%d H=%d W=%d Cin=%d)", (int)cr, d->N,
                    d->H, d->W, d->Cin);
     return TECO_E_CUDA;
   }
-  static size_t smem_set = 0;
-  if (smem_bytes > smem_set) {
-    TECO_CUDA_CALL(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    smem_set = 220 * 1024;
+  using KernelT = void (*)(const CUtensorMap, const TcParams);
+  KernelT kern = nullptr;
+#define TECO_PICK(M, T, JJ, K) if (d->mode == M && p.TPS == T && J == JJ && p.KS == K) kern = conv3x3_tc_kernel<M, T, JJ, K>;
+  TECO_PICK(0, 3, 1, 3) TECO_PICK(0, 3, 2, 3) TECO_PICK(0, 3, 1, 1) TECO_PICK(0, 3, 2, 1) TECO_PICK(0, 1, 1, 1) TECO_PICK(0, 1, 2, 1)
+  TECO_PICK(1, 3, 1, 1) TECO_PICK(1, 3, 2, 1) TECO_PICK(1, 1, 1, 1) TECO_PICK(1, 1, 2, 1)
+#undef TECO_PICK
+  if (!kern) {
+    teco_set_error("teco_conv3x3_tc: no kernel instantiation for mode=%d TPS=%d J=%d KS=%d", d->mode, p.TPS, J, p.KS);
+    return TECO_E_UNSUPPORTED;
   }
+  TECO_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
   const unsigned ctas = (unsigned)((p.num_tiles + p.CS - 1) / p.CS * p.CS);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);
@@ -558,11 +624,10 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, tmap, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, p);
   if (le != cudaSuccess) {
     teco_set_error("teco_conv3x3_tc: launch failed: %s (grid %u, cluster %d, smem %zu)", cudaGetErrorString(le), ctas, p.CS, smem_bytes);
     return TECO_E_CUDA;
   }
-  TECO_CUDA_LAUNCH_CHECK("teco_conv3x3_tc");
   return TECO_OK;
 }

@@ -24,6 +24,11 @@ def pad16(c):
     return (c + 15) // 16 * 16
 
 
+def pad64(c):
+    """bf16 activation tensors carry multiples of 64 channels: 64 ch = one 128-byte swizzled UMMA/TMA row."""
+    return (c + 63) // 64 * 64
+
+
 class TcLayer:
     __slots__ = ("wpk", "bias", "cin_pad", "cout_pad", "cout")
 
@@ -31,7 +36,7 @@ class TcLayer:
 _cache = {}
 
 
-def _layer(full_name, transpose=False, cin_perm=None, cin_pad=None):
+def _layer(full_name, transpose=False, cin_perm=None, cin_pad=None, f32_out=False):
     """Packed weights for variable scope `full_name` (…/Conv or …/Conv2d_transpose), cached per store version."""
     store = default_store()
     key = (id(store), store.version, full_name)
@@ -45,8 +50,8 @@ def _layer(full_name, transpose=False, cin_perm=None, cin_pad=None):
     else:
         cin, cout = w.shape[2], w.shape[3]
     L = TcLayer()
-    L.cin_pad = cin_pad or pad16(cin)
-    L.cout_pad = pad16(cout)
+    L.cin_pad = cin_pad or pad64(cin)
+    L.cout_pad = pad16(cout) if f32_out else pad64(cout)
     L.cout = cout
     L.wpk = K.packed_weight(w.detach(), L.cin_pad, L.cout_pad, transpose, cin_perm)
     L.bias = K.pad_bias(b.detach(), L.cout_pad) if b is not None else None
@@ -110,7 +115,7 @@ class GeneratorPlan:
                       for i in range(1, num_resblock + 1)]
         self.l_t1 = _layer(g + "conv_tran2highres/conv_tran1/Conv2d_transpose", transpose=True)
         self.l_t2 = _layer(g + "conv_tran2highres/conv_tran2/Conv2d_transpose", transpose=True)
-        self.l_out = _layer(g + "output_stage/conv/Conv")
+        self.l_out = _layer(g + "output_stage/conv/Conv", f32_out=True)
         z = lambda *s: torch.zeros(s, device=device, dtype=bf16)
         self.x_in = z(B, h, w, 64)            # packed generator input (zero pad channels stay zero)
         self.a = z(B, h, w, 64)
@@ -147,20 +152,21 @@ class FNetPlan:
         for name, _, _ in FNET_SPEC:
             self.layers.append((_layer(f + name + "/conv_1/Conv"), _layer(f + name + "/conv_2/Conv")))
         self.l_o1 = _layer(f + "output_stage/conv1/Conv")
-        self.l_o2 = _layer(f + "output_stage/conv2/Conv")
+        self.l_o2 = _layer(f + "output_stage/conv2/Conv", f32_out=True)
         z = lambda *s: torch.zeros(s, device=device, dtype=bf16)
-        self.x_in = z(n, h, w, 16)            # prev RGB (0..2), cur RGB (3..5), zeros
+        self.x_in = z(n, h, w, 64)            # prev RGB (0..2), cur RGB (3..5), zeros
         self.bufs = []
         ch, cw = h, w
         for i, (name, _, cout) in enumerate(FNET_SPEC):
-            t1, t2 = z(n, ch, cw, cout), z(n, ch, cw, cout)
+            cp = pad64(cout)
+            t1, t2 = z(n, ch, cw, cp), z(n, ch, cw, cp)
             if i < 3:
                 ch, cw = ch // 2, cw // 2
             else:
                 ch, cw = ch * 2, cw * 2
-            self.bufs.append((t1, t2, z(n, ch, cw, cout)))
+            self.bufs.append((t1, t2, z(n, ch, cw, cp)))
         self.fh, self.fw = ch, cw
-        self.o1 = z(n, ch, cw, 32)
+        self.o1 = z(n, ch, cw, 64)
         self.flow = torch.zeros((n, ch, cw, 2), device=device, dtype=f32)
         self.launches = 14 + 6
 
@@ -176,7 +182,7 @@ class FNetPlan:
             else:
                 call("teco_resize2x_bf16", ptr(t2, bf16), ptr(t3, bf16), n, hh, ww, cc, stream_ptr())
             x = t3
-        K.conv3x3_tc(x, self.l_o1.wpk, self.l_o1.bias, self.o1, cout=32, act=ACT_LRELU02)
+        K.conv3x3_tc(x, self.l_o1.wpk, self.l_o1.bias, self.o1, cout=64, act=ACT_LRELU02)
         K.conv3x3_tc(self.o1, self.l_o2.wpk, self.l_o2.bias, None, cout=16, act=ACT_TANH24, out_f32=self.flow)
         return self.flow
 

@@ -232,6 +232,18 @@ def _bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def _p64(c):
+    return (c + 63) // 64 * 64
+
+
+def _xpad(x):
+    """NHWC fp32 -> bf16 CUDA tensor with the channel count zero-padded to a multiple of 64 (the kernel's layout)."""
+    n, h, w, c = x.shape
+    out = torch.zeros(n, h, w, _p64(c), dtype=torch.bfloat16, device="cuda")
+    out[..., :c] = x.cuda().to(torch.bfloat16)
+    return out
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,act", [
     (1, 16, 8, 64, 64, 0), (1, 32, 32, 64, 64, 1), (2, 48, 40, 64, 64, 2), (1, 19, 21, 16, 32, 2), (1, 32, 32, 32, 64, 0),
     (1, 16, 16, 128, 256, 2), (1, 16, 24, 256, 128, 2), (1, 64, 64, 64, 16, 0), (1, 128, 128, 64, 64, 1), (3, 32, 32, 128, 128, 0),
@@ -241,13 +253,13 @@ def test_conv3x3_tc_matches_oracle_on_bf16_operands(n, h, w, cin, cout, act):
     x, wt, b = _bf(rnd(1, n, h, w, cin)), _bf(rnd(2, 3, 3, cin, cout) * (2.0 / (9 * cin) ** 0.5)), rnd(3, cout) * 0.1
     acts = {0: lambda v: v, 1: torch.relu, 2: O.lrelu}
     ref = acts[act](O.conv2d(x, wt, b))
-    wpk = K.packed_weight(dev(wt), cin, cout)
-    got = K.conv3x3_tc(dev(x).to(torch.bfloat16), wpk, dev(b), cout=cout, act=act)
+    wpk = K.packed_weight(dev(wt), _p64(cin), cout)
+    got = K.conv3x3_tc(_xpad(x), wpk, dev(b), cout=cout, act=act)
     torch.cuda.synchronize()
     assert_close(got, ref, 2e-3, 1.0 / 128, what="conv3x3_tc")
     # residual add
     res = _bf(rnd(4, n, h, w, cout))
-    got = K.conv3x3_tc(dev(x).to(torch.bfloat16), wpk, dev(b), cout=cout, act=0, res=dev(res).to(torch.bfloat16))
+    got = K.conv3x3_tc(_xpad(x), wpk, dev(b), cout=cout, act=0, res=dev(res).to(torch.bfloat16))
     assert_close(got, O.conv2d(x, wt, b) + res, 2e-3, 1.0 / 128, what="conv3x3_tc+res")
 
 
@@ -276,8 +288,8 @@ def test_conv3x3_tc_fp32_output_stage():
 def test_abi_rejects_bad_arguments_with_valueerror():
     from tecogan_b200 import kernels as K
     with pytest.raises(ValueError):
-        K.conv3x3_tc(torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.bfloat16),
-                     torch.zeros(9 * 24 * 16, device="cuda", dtype=torch.bfloat16), None, cout=16)
+        K.conv3x3_tc(torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16),
+                     torch.zeros(9 * 48 * 16, device="cuda", dtype=torch.bfloat16), None, cout=16)
     with pytest.raises(ValueError):
         K.dense_image_warp(torch.zeros(1, 8, 8, 3, device="cuda"), torch.zeros(1, 8, 7, 2, device="cuda"))
     with pytest.raises(ValueError):
