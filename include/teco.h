@@ -175,6 +175,8 @@ int teco_loss_l1_f32(const float* a, const float* b, float* out, float* da, floa
 /* VGG cosine term :346-349 on raw features f,g [npix,C]: 1 - mean_pix( <f,g> / (|f|_eps |g|_eps) ) */
 int teco_loss_cosine_f32(const float* f, const float* g, float* out, float* df, int64_t npix, int32_t C, float gscale,
                          void* stream);
+/* per-pixel channel L2 normalisation of VGG features, lib/Teco.py:19-21: y = f / sqrt(sum_c f^2 + 1e-12) */
+int teco_l2norm_channels_f32(const float* f, float* y, int64_t npix, int32_t C, void* stream);
 /* GAN terms :376,394-399 on sigmoid outputs.  out[0]=mean -log(df+eps)  out[1]=mean -(log(1-df+eps)+log(dr+eps))
  * out[2]=mean log(dr+eps)  out[3]=mean dr  out[4]=mean df.  Gradients w.r.t. the sigmoid OUTPUTS:
  * g_adv = d(out0*s_adv)/d df ; g_dis_f, g_dis_r = d(out1*s_dis)/d(df,dr). */

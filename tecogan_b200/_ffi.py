@@ -66,6 +66,7 @@ SIGNATURES = {
     "teco_loss_l2_f32": [_P, _P, _P, _P, _I64, _I32, _F, _P],
     "teco_loss_l1_f32": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
     "teco_loss_cosine_f32": [_P, _P, _P, _P, _I64, _I32, _F, _P],
+    "teco_l2norm_channels_f32": [_P, _P, _I64, _I32, _P],
     "teco_loss_gan_f32": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _P],
     "teco_adam_f32": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P],
 }

@@ -381,3 +381,27 @@ int teco_adam_f32(float* p, float* m, float* v, const float* g, int64_t n, float
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// per-pixel channel L2 normalisation of VGG features (reference lib/Teco.py:19-21): y = f / sqrt(sum_c f^2 + 1e-12)
+namespace {
+__global__ void l2norm_channels_kernel(const float* __restrict__ f, float* __restrict__ y, long long npix, int C) {
+  int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < npix; p += nwarps) {
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { float v = f[p * C + c]; ss += v * v; }
+    ss = warp_sum(ss);
+    float inv = 1.0f / sqrtf(ss + 1e-12f);
+    for (int c = lane; c < C; c += 32) y[p * C + c] = f[p * C + c] * inv;
+  }
+}
+}  // namespace
+
+extern "C" int teco_l2norm_channels_f32(const float* f, float* y, int64_t npix, int32_t C, void* stream) {
+  TECO_CHECK_ARG(f && y && npix > 0 && C > 0, "teco_l2norm_channels_f32: bad argument");
+  l2norm_channels_kernel<<<grid_for(npix * 32), TPB, 0, (cudaStream_t)stream>>>(f, y, npix, C);
+  TECO_CUDA_LAUNCH_CHECK("teco_l2norm_channels_f32");
+  return TECO_OK;
+}

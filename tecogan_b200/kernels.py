@@ -338,7 +338,7 @@ class _LossL2(torch.autograd.Function):
         a, b = _cc(a), _cc(b)
         C = a.shape[-1]
         out = torch.empty(1, device=a.device, dtype=f32)
-        da = torch.empty_like(a) if a.requires_grad or b.requires_grad else None
+        da = torch.empty_like(a) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
         call("teco_loss_l2_f32", ptr(a, f32), ptr(b, f32), ptr(out, f32), ptr(da, f32), a.numel() // C, C, 1.0, stream_ptr())
         ctx.save_for_backward(da)
         return out[0]
@@ -361,7 +361,7 @@ class _LossL1(torch.autograd.Function):
         a, b = _cc(a), _cc(b)
         C = a.shape[-1]
         out = torch.empty(1, device=a.device, dtype=f32)
-        da = torch.empty_like(a) if a.requires_grad or b.requires_grad else None
+        da = torch.empty_like(a) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
         call("teco_loss_l1_f32", ptr(a, f32), ptr(b, f32), ptr(out, f32), ptr(da, f32), ptr(None), a.numel() // C, C,
              int(per_pixel), 1.0, stream_ptr())
         ctx.save_for_backward(da)
@@ -385,7 +385,7 @@ class _LossCos(torch.autograd.Function):
         f, g = _cc(f), _cc(g)
         C = f.shape[-1]
         out = torch.empty(1, device=f.device, dtype=f32)
-        df = torch.empty_like(f) if f.requires_grad else None
+        df = torch.empty_like(f) if ctx.needs_input_grad[0] else None
         call("teco_loss_cosine_f32", ptr(f, f32), ptr(g, f32), ptr(out, f32), ptr(df, f32), f.numel() // C, C, 1.0, stream_ptr())
         ctx.save_for_backward(df)
         return out[0]
@@ -455,6 +455,14 @@ def gauss_down4(hr):
 def to_u8(x01):
     y = torch.empty(x01.shape, device=x01.device, dtype=torch.uint8)
     call("teco_to_u8", ptr(_cc(x01), f32), ptr(y, torch.uint8), x01.numel(), stream_ptr())
+    return y
+
+
+def l2norm_channels(f):
+    """f / sqrt(sum_c f^2 + 1e-12) per pixel (VGG19_slim norm_flag, reference lib/Teco.py:19-21); forward only."""
+    f = _cc(f.detach())
+    y = torch.empty_like(f)
+    call("teco_l2norm_channels_f32", ptr(f, f32), ptr(y, f32), f.numel() // f.shape[-1], f.shape[-1], stream_ptr())
     return y
 
 

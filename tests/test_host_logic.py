@@ -1,0 +1,111 @@
+"""CPU: host-side logic of the mirror -- variable scopes / TF variable names, flag parsing, sub-pixel phase
+decomposition of the stride-2 transposed conv, clip sharding and the 2-rank gloo all-reduce of the gradient bucket."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import teco_oracle as O
+
+
+def test_variable_scopes_produce_tf_variable_names():
+    from tecogan_b200 import variables as V
+    st = V.set_default_store(V.VariableStore(device="cpu"))
+    with V.variable_scope('generator'), V.variable_scope('generator_unit'), V.variable_scope('resblock_3'):
+        with V.variable_scope('conv_1'), V.variable_scope('Conv'):
+            w = V.get_variable('weights', (3, 3, 64, 64), fans=(576, 576))
+            b = V.get_variable('biases', (64,), init='zeros')
+            assert V.get_variable('weights', (3, 3, 64, 64), fans=(576, 576)) is w       # reuse
+            with pytest.raises(ValueError):
+                V.get_variable('weights', (3, 3, 64, 32), fans=(576, 288))
+    assert list(st) == ['generator/generator_unit/resblock_3/conv_1/Conv/weights',
+                        'generator/generator_unit/resblock_3/conv_1/Conv/biases']
+    assert float(w.abs().max()) <= (6.0 / 1152) ** 0.5 + 1e-7 and float(b.abs().max()) == 0.0
+
+
+def test_init_params_cover_the_same_names_as_the_oracle():
+    from tecogan_b200.init_params import xavier_params
+    p = xavier_params(3, num_resblock=16, need_d=True, need_vgg=True)
+    ref = {}
+    for d in (O.init_generator(), O.init_fnet(), O.init_discriminator(), O.init_vgg19()):
+        ref.update(d)
+    assert set(p) == set(ref)
+    for k in p:
+        assert tuple(p[k].shape) == tuple(ref[k].shape), k
+
+
+def test_flag_parsing_follows_tf_app_flags_conventions():
+    import main
+    F_ = main.parse_flags(['--mode', 'train', '--nopingpang', '--stair', '--ratio', '-0.01', '--output_dir', '/tmp/x',
+                           '--Dt_mergeDs', '--learning_rate=0.00005', '--num_resblock', '10'])
+    assert (F_.pingpang, F_.stair, F_.ratio, F_.Dt_mergeDs, F_.learning_rate, F_.num_resblock) == (False, True, -0.01, True, 5e-5, 10)
+    assert F_.crop_dt == 0.75 and F_.Dbalance == 0.4 and F_.RNN_N == 10 and F_.EPS == 1e-12   # reference defaults
+
+
+@pytest.mark.parametrize("K,pad", [(3, 0), (4, 1)])
+def test_transposed_conv_phase_decomposition(K, pad):
+    """kernels._phase_taps + the phase-weight slicing of conv_transpose2x_raw, emulated with torch-CPU convs, equals
+    the oracle's conv2d_transpose (K=3, pad 0) / the input gradient of a stride-2 SAME conv (K=4, pad 1)."""
+    from tecogan_b200.kernels import _phase_taps
+    torch.manual_seed(0)
+    n, h, w, cin, cout = 2, 5, 6, 3, 4
+    x = torch.randn(n, h, w, cin)
+    w_oi = torch.randn(K, K, cout, cin)
+    y = torch.zeros(n, 2 * h, 2 * w, cout)
+    for a in (0, 1):
+        kys, pt = _phase_taps(K, pad, a)
+        for b in (0, 1):
+            kxs, pl = _phase_taps(K, pad, b)
+            wp = w_oi[kys][:, kxs].permute(0, 1, 3, 2)                        # [ty,tx,ci,co]
+            xp = F.pad(x.permute(0, 3, 1, 2), (pl, len(kxs) - 1 - pl, pt, len(kys) - 1 - pt))
+            y[:, a::2, b::2] = F.conv2d(xp, wp.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+    if K == 3:
+        ref = O.conv2d_transpose(x, w_oi)
+    else:
+        inp = torch.zeros(n, 2 * h, 2 * w, cout, requires_grad=True)
+        (ref,) = torch.autograd.grad(O.conv2d(inp, w_oi, None, stride=2), inp, x)   # w_oi as HWIO with I=cout
+    assert (y - ref).abs().max().item() < 1e-5
+
+
+def test_clip_sharding_is_balanced_and_complete():
+    from tecogan_b200.parallel import shard_clips
+    for n, w in ((8, 8), (10, 4), (3, 8), (32, 8)):
+        spans = [shard_clips(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _dp_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from tecogan_b200.parallel import allreduce_bucket, decide_with_d
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)
+    bucket = torch.cat((torch.randn(1000), torch.tensor([0.3 + 0.4 * rank, 1.0 + rank])))   # grads | t_balance | loss
+    mine = bucket.clone()
+    inv = allreduce_bucket(bucket)
+    tb_ema = 0.0
+    decisions = []
+    for _ in range(3):
+        with_d, tb_ema = decide_with_d(tb_ema, float(bucket[1000]) * inv, 0.004)
+        decisions.append(with_d)
+    ret[rank] = (mine.numpy(), bucket.numpy(), inv, decisions, tb_ema)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_bucket_and_identical_control_flow():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(2, port, ret), nprocs=2, join=True)
+    (m0, b0, inv0, d0, e0), (m1, b1, inv1, d1, e1) = ret[0], ret[1]
+    assert inv0 == inv1 == 0.5
+    np.testing.assert_allclose(b0, m0 + m1, rtol=1e-6)
+    np.testing.assert_array_equal(b0, b1)                    # every rank holds the same reduced bucket
+    assert d0 == d1 and e0 == e1                             # hence the same with-D / without-D branch every step
+    assert d0 == [True, False, False]                        # EMA(0.01 * 0.5) crosses Dbalance=0.004 after one update
