@@ -23,8 +23,10 @@
 // Why SW128 and not the no-swizzle layout (round-1 measurement, profiles/conv_tc_r01_notes.md): with 16-byte core
 // matrix rows every tcgen05.mma took ~250 cycles instead of ~32-48, and the 16-byte TMA rows ran at ~10 B/clk/SM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue
+// (one epilogue warp per scheduler is latency-bound: ~1000 clk per 32 channels; two per scheduler halve it).
 #include <cuda.h>
+#include <type_traits>
 #include "teco_common.cuh"
 
 namespace {
@@ -33,10 +35,12 @@ constexpr int TILE_ROWS = 16;
 constexpr int HALO_ROWS = TILE_ROWS + 2;
 constexpr int CB = 64;                 // channels per K block = one 128-byte swizzled row
 constexpr int MAX_WST = 12;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;       // two warps per TMEM lane quarter, each taking half of the output channels
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct TcParams {
-  int N, H, W, Cin, Cout;
+  int N, H, W, Cin, Cout;             // Cout = channel pitch of y / res / bias (all output channels)
+  int Ncta, nsplit, tiles_pad;        // output channels per CTA (UMMA N), Cout splits, tile count padded to the cluster size
   int tiles_x, tiles_y, J;
   int mode, act, out_f32_c;
   float post_scale, post_shift;
@@ -137,6 +141,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
@@ -157,7 +171,7 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // They are compile-time so that the MMA issue loop is a fully unrolled stream of UTCHMMA whose descriptors differ
 // from per-stage bases by immediates (uniform-datapath adds, no per-instruction R2UR).
 template <int MODE, int TPS, int J, int KS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -175,8 +189,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   float* s_bias = reinterpret_cast<float*>(bars + 4 + 2 * MAX_WST + 2);   // [Cout]
 
   // tile coordinates
-  int tile = blockIdx.x;
-  const bool active = tile < p.num_tiles;    // grid is padded to a multiple of the cluster size
+  int tile = blockIdx.x % p.tiles_pad;      // grid = nsplit x (tiles padded to a multiple of the cluster size)
+  const int n0 = (blockIdx.x / p.tiles_pad) * p.Ncta;   // first output channel of this CTA (all CTAs of a cluster share it)
+  const bool active = tile < p.num_tiles;
   if (!active) tile = 0;
   const int tx = tile % p.tiles_x;
   tile /= p.tiles_x;
@@ -222,55 +237,72 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (p.mcast) {
-        // Weights do not depend on the previous layer: fetch them before the dependency wait.  Each CTA of the
-        // cluster fetches 1/CS of every slab and multicasts it to all CS CTAs (one L2 read per cluster).
+    // Issue cost of one bulk/tensor copy is a few hundred cycles, so independent copies are issued by different lanes.
+    if (p.mcast) {
+      // Weights do not depend on the previous layer: fetch them before the dependency wait.  Each CTA of the
+      // cluster fetches 1/CS of every slab and multicasts it to all CS CTAs (one L2 read per cluster).
+      const int sidx = lane;
+      if (sidx < slabs_per_blk * p.nblk) {
         const uint32_t crank = p.CS > 1 ? cluster_ctarank() : 0;
         const uint32_t part = p.w_slab_bytes / (uint32_t)p.CS;
         const uint16_t mask = (uint16_t)((1u << p.CS) - 1u);
-        for (int sidx = 0; sidx < slabs_per_blk * p.nblk; ++sidx) {
-          const int b = sidx / slabs_per_blk, g = sidx - slabs_per_blk * b;
-          mbar_expect_tx(smem_u32(&w_full[sidx]), p.w_slab_bytes);
-          // global layout [blk][tap][cout][64]: a slab = TPS consecutive taps of one block
-          const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout) * 128 + (size_t)crank * part;
-          const uint32_t dst = smem_u32(w_base + (size_t)sidx * p.w_slab_bytes) + crank * part;
-          if (p.CS > 1) bulk_load_1d_mcast(dst, src, part, smem_u32(&w_full[sidx]), mask);
-          else bulk_load_1d(dst, src, part, smem_u32(&w_full[sidx]));
-        }
+        const int b = sidx / slabs_per_blk, g = sidx - slabs_per_blk * b;
+        mbar_expect_tx(smem_u32(&w_full[sidx]), p.w_slab_bytes);
+        // global layout [blk][tap][cout][64]: a slab = TPS consecutive taps of one block (TPS == 3 only when nsplit == 1)
+        const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout + n0) * 128 + (size_t)crank * part;
+        const uint32_t dst = smem_u32(w_base + (size_t)sidx * p.w_slab_bytes) + crank * part;
+        if (p.CS > 1) bulk_load_1d_mcast(dst, src, part, smem_u32(&w_full[sidx]), mask);
+        else bulk_load_1d(dst, src, part, smem_u32(&w_full[sidx]));
       }
-      STAMP(9);
-      pdl_wait();   // the previous kernel's output (our input x) is complete and visible from here on
-      STAMP(10);
-      if (active) {
-        int hs = 0, ws = 0;
-        uint32_t hph = 0, wph = 0;
-        for (int b = 0; b < p.nblk; ++b) {
+      __syncwarp();
+    }
+    // Ring mode: the first WST weight slabs do not depend on the previous layer either -> issue them before the wait.
+    const int total_slabs = slabs_per_blk * p.nblk;
+    int next_slab = 0;
+    if (!p.mcast && lane == 0) {
+      for (; next_slab < total_slabs && next_slab < p.WST; ++next_slab) {
+        const int b = next_slab / slabs_per_blk, g = next_slab - slabs_per_blk * b;
+        mbar_expect_tx(smem_u32(&w_full[next_slab]), p.w_slab_bytes);
+        const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout + n0) * 128;
+        bulk_load_1d(smem_u32(w_base + (size_t)next_slab * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[next_slab]));
+      }
+    }
+    if (lane == 0) STAMP(9);
+    pdl_wait();   // the previous kernel's output (our input x) is complete and visible from here on
+    if (lane == 0) STAMP(10);
+    if (active) {
+      int hs = 0;
+      uint32_t hph = 0;
+      for (int b = 0; b < p.nblk; ++b) {
+        if (lane == 0) {
           mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
           mbar_expect_tx(smem_u32(&halo_full[hs]), copy_bytes * ncopies);
-          for (int c = 0; c < ncopies; ++c)
-            tma_load_4d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes + (size_t)c * copy_bytes), &tmap,
-                        smem_u32(&halo_full[hs]), b * CB, x0 - 1 + c, y0 - 1, n);
-          if (!p.mcast) {
-            for (int g = 0; g < slabs_per_blk; ++g) {
-              mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
-              mbar_expect_tx(smem_u32(&w_full[ws]), p.w_slab_bytes);
-              const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout) * 128;
-              bulk_load_1d(smem_u32(w_base + (size_t)ws * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[ws]));
-              if (++ws == p.WST) { ws = 0; wph ^= 1; }
-            }
-          }
-          if (++hs == p.HST) { hs = 0; hph ^= 1; }
         }
-      } else if (p.mcast) {
-        // padding CTA of a cluster: it only relays its share of the weights; stay until they have landed here too
-        for (int sidx = 0; sidx < slabs_per_blk * p.nblk; ++sidx) mbar_wait(smem_u32(&w_full[sidx]), 0);
+        __syncwarp();
+        if (lane < ncopies)
+          tma_load_4d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes + (size_t)lane * copy_bytes), &tmap,
+                      smem_u32(&halo_full[hs]), b * CB, x0 - 1 + lane, y0 - 1, n);
+        if (!p.mcast && lane == 0) {
+          for (; next_slab < (b + 1) * slabs_per_blk; ++next_slab) {   // slabs of this block not yet in flight
+            const int st = next_slab % p.WST, use = next_slab / p.WST;
+            const int g = next_slab - slabs_per_blk * b;
+            mbar_wait(smem_u32(&w_empty[st]), (uint32_t)((use - 1) & 1));   // the MMAs of the previous use have retired
+            mbar_expect_tx(smem_u32(&w_full[st]), p.w_slab_bytes);
+            const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout + n0) * 128;
+            bulk_load_1d(smem_u32(w_base + (size_t)st * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[st]));
+          }
+        }
+        __syncwarp();
+        if (++hs == p.HST) { hs = 0; hph ^= 1; }
       }
+    } else if (p.mcast && lane == 0) {
+      // padding CTA of a cluster: it only relays its share of the weights; stay until they have landed here too
+      for (int sidx = 0; sidx < slabs_per_blk * p.nblk; ++sidx) mbar_wait(smem_u32(&w_full[sidx]), 0);
     }
     __syncwarp();
   } else if (warp == 1 && active) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc(p.Cout);
+    const uint32_t idesc = umma_idesc(p.Ncta);
     constexpr uint32_t a_sbo = (uint32_t)row_bytes;   // next 8-pixel group of the M=128 sub-tile = next image row
     constexpr uint32_t b_sbo = 1024u;                 // next 8 output channels
     int hs = 0, ws = 0;
@@ -290,7 +322,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           const uint32_t slab_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
           const uint64_t a_base = umma_desc_sw128(halo_addr, a_sbo);
           const uint64_t b_base = umma_desc_sw128(slab_addr, b_sbo);
-          const uint32_t tap_stride16 = (uint32_t)(p.Cout * 128) >> 4;   // weight bytes per tap, in descriptor units
+          const uint32_t tap_stride16 = (uint32_t)(p.Ncta * 128) >> 4;   // weight bytes per tap, in descriptor units
           // per-tap row/copy/phase (TPS == 3: ky = g, kx = tt; TPS == 1: tap = g)
           uint32_t a_off16[TPS], acc_idx[TPS];
 #pragma unroll
@@ -324,7 +356,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 #pragma unroll
                     for (int t2 = 0; t2 < tt; ++t2) accum |= (acc_idx[t2] == acc_idx[tt]) ? 1u : 0u;
                   }
-                  umma_bf16(tmem_base + acc * (uint32_t)p.Cout, a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
+                  umma_bf16(tmem_base + acc * (uint32_t)p.Ncta, a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
                             b_base + tt * tap_stride16 + (uint32_t)((s * 32) >> 4), idesc, accum);
                 }
               }
@@ -349,11 +381,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     __syncwarp();
   } else if (warp >= 2 && active) {
     // ===================== epilogue (warps 2..5) =====================
-    for (int c = (int)threadIdx.x - 64; c < p.Cout; c += 128) s_bias[c] = p.bias ? p.bias[c] : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    for (int c = (int)threadIdx.x - 64; c < p.Ncta; c += 32 * NUM_EPI_WARPS) s_bias[c] = p.bias ? p.bias[n0 + c] : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");   // the epilogue warps only
     pdl_wait();                                        // res / y belong to the dependency chain
     if (threadIdx.x == 64) STAMP(25);
     const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2; // which half of the channel steps this warp takes (0 or 1)
     const int m = 32 * q + lane;       // accumulator row = pixel within the 16x8 sub-tile
     const int ry = m >> 3, rx = m & 7;
     const float act_slope = p.act == TECO_ACT_RELU ? 0.f : (p.act == TECO_ACT_LRELU02 ? 0.2f : 1.f);
@@ -361,80 +394,91 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     tcgen05_fence_after();
     if (threadIdx.x == 64) STAMP(6);
     const int oy_in = y0 + ry;
-    for (int j = 0; j < J; ++j) {
-      const int ox_in = x0 + 8 * j + rx;
-      const bool in_img = (oy_in < p.H) && (ox_in < p.W);
-      for (int ph = 0; ph < nacc; ++ph) {
-        int oy, ox, OH, OW;
-        if (MODE == 1) {
-          oy = 2 * oy_in + (ph >> 1); ox = 2 * ox_in + (ph & 1); OH = 2 * p.H; OW = 2 * p.W;
-        } else {
-          oy = oy_in; ox = ox_in; OH = p.H; OW = p.W;
-        }
-        const size_t pix = ((size_t)n * OH + oy) * OW + ox;
-        const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((j * nacc + ph) * KS * p.Cout);
-        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-          uint32_t r[16];
-          __syncwarp();
-          tmem_ld16(tcol + (uint32_t)c0, r);
-          if (KS == 3) {   // K-split chains: issue all three TMEM loads, wait once, add
-            uint32_t r2[16], r3[16];
-            tmem_ld16(tcol + (uint32_t)(p.Cout + c0), r2);
-            tmem_ld16(tcol + (uint32_t)(2 * p.Cout + c0), r3);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]) + __uint_as_float(r3[i]));
+    // EW output channels per step: 32 (two steps for 64 channels) or 16 (the 16-channel fp32 output stage)
+    auto run = [&](auto ew_tag) {
+      constexpr int EW = decltype(ew_tag)::value;
+      for (int j = 0; j < J; ++j) {
+        const int ox_in = x0 + 8 * j + rx;
+        const bool in_img = (oy_in < p.H) && (ox_in < p.W);
+        for (int ph = 0; ph < nacc; ++ph) {
+          int oy, ox, OH, OW;
+          if (MODE == 1) {
+            oy = 2 * oy_in + (ph >> 1); ox = 2 * ox_in + (ph & 1); OH = 2 * p.H; OW = 2 * p.W;
           } else {
-            tmem_wait_ld();
+            oy = oy_in; ox = ox_in; OH = p.H; OW = p.W;
           }
-          if (threadIdx.x == 64 && j == 0 && ph == 0 && c0 == 0) STAMP(11);
-          float v[16];
+          const size_t pix = ((size_t)n * OH + oy) * OW + ox;
+          const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((j * nacc + ph) * KS * p.Ncta);
+          for (int c0 = chalf * EW; c0 < p.Ncta; c0 += 2 * EW) {
+            uint32_t r[EW];
+            __syncwarp();
+            if (EW == 32) tmem_ld32(tcol + (uint32_t)c0, r); else tmem_ld16(tcol + (uint32_t)c0, r);
+            if (KS == 3) {   // K-split chains: issue all three TMEM loads, wait once, add
+              uint32_t r2[EW], r3[EW];
+              if (EW == 32) { tmem_ld32(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld32(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
+              else { tmem_ld16(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld16(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
+              tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = __uint_as_float(r[i]) + s_bias[c0 + i];
-            v[i] = fmaxf(a, a * act_slope);      // none: slope 1, relu: 0, lrelu: 0.2 -- no per-element branch
-          }
-          if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop
+              for (int i = 0; i < EW; ++i)
+                r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]) + __uint_as_float(r3[i]));
+            } else {
+              tmem_wait_ld();
+            }
+            if (threadIdx.x == 64 && j == 0 && ph == 0 && c0 == 0) STAMP(11);
+            float v[EW];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = teco_act(v[i], p.act);
-          }
-          if (!in_img) continue;
-          if (p.out_f32) {
-            for (int i = 0; i < 16; ++i) {
-              int c = c0 + i;
-              if (c < p.out_f32_c) {
-                float a = v[i] + (p.res_f32 ? p.res_f32[pix * p.out_f32_c + c] : 0.f);
-                p.out_f32[pix * p.out_f32_c + c] = a * p.post_scale + p.post_shift;
+            for (int i = 0; i < EW; ++i) {
+              const float a = __uint_as_float(r[i]) + s_bias[c0 + i];
+              v[i] = fmaxf(a, a * act_slope);      // none: slope 1, relu: 0, lrelu: 0.2 -- no per-element branch
+            }
+            if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop
+#pragma unroll
+              for (int i = 0; i < EW; ++i) v[i] = teco_act(v[i], p.act);
+            }
+            if (!in_img) continue;
+            if (p.out_f32) {
+              for (int i = 0; i < EW; ++i) {
+                int c = n0 + c0 + i;
+                if (c < p.out_f32_c) {
+                  float a = v[i] + (p.res_f32 ? p.res_f32[pix * p.out_f32_c + c] : 0.f);
+                  p.out_f32[pix * p.out_f32_c + c] = a * p.post_scale + p.post_shift;
+                }
               }
             }
-          }
-          if (p.y) {
-            if (p.res) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + c0);
-              uint4 r0 = rp[0], r1 = rp[1];
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            if (p.y) {
+              if (p.res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + n0 + c0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
-                v[2 * i] += f.x;
-                v[2 * i + 1] += f.y;
+                for (int k = 0; k < EW / 8; ++k) {
+                  const uint4 rr = rp[k];
+                  const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+                    v[8 * k + 2 * i] += f.x;
+                    v[8 * k + 2 * i + 1] += f.y;
+                  }
+                }
+              }
+              uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.Cout + n0 + c0);
+#pragma unroll
+              for (int k = 0; k < EW / 8; ++k) {
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                  o[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                yp[k] = make_uint4(o[0], o[1], o[2], o[3]);
               }
             }
-            uint32_t o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              o[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.Cout + c0);
-            yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            if (threadIdx.x == 64 && j == 0 && ph == 0) STAMP(12 + ((c0 / EW) & 3));
           }
-          if (threadIdx.x == 64 && j == 0 && ph == 0) STAMP(12 + (c0 >> 4 & 3));
         }
       }
-    }
+    };
+    if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});
+    else run(std::integral_constant<int, 16>{});
   }
 
   if (threadIdx.x == 64) STAMP(7);
@@ -535,32 +579,53 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.res_f32 = res_f32; p.out_f32 = out_f32; p.dbg = g_dbg_timing;
   p.nblk = d->Cin / CB;
   p.HST = p.nblk > 1 ? 2 : 1;
+  // few spatial tiles but many output channels (FNet's 16x16 / 32x32 layers): split Cout over CTAs, 64 channels each
+  {
+    long long t1 = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8);
+    p.nsplit = (d->Cout >= 128 && d->Cout % 64 == 0 && t1 * (d->Cout / 64) <= 2LL * teco_sm_count()) ? d->Cout / 64 : 1;
+    p.Ncta = d->Cout / p.nsplit;
+  }
   const int nacc = d->mode == 1 ? 4 : 1;
   const size_t budget = 208 * 1024;
   const int sms = teco_sm_count();
   // sub-tiles per CTA: prefer the wider tile when it still yields >= 2 waves of CTAs and fits TMEM / smem
   int J = 1;
   for (int j = 2; j >= 1; --j) {
-    if (j * nacc * d->Cout > 512) continue;
+    if (j * nacc * p.Ncta > 512) continue;
     size_t a_bytes = (size_t)p.HST * 3 * HALO_ROWS * 8 * j * 128;
-    if (a_bytes + 2 * (size_t)d->Cout * 128 > budget) continue;
+    if (a_bytes + 2 * (size_t)p.Ncta * 128 > budget) continue;
     long long tiles = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8 * j);
     if (tiles >= 2LL * sms || j == 1) { J = j; break; }
   }
-  TECO_CHECK_ARG(J * nacc * d->Cout <= 512, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
+  TECO_CHECK_ARG(J * nacc * p.Ncta <= 512, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
   p.J = J;
   p.tiles_x = teco_ceil_div(d->W, 8 * J);
   p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
   p.copy_bytes = (uint32_t)(HALO_ROWS * 8 * J * 128);
   p.halo_stage_bytes = 3 * p.copy_bytes;
   const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
-  const size_t tap_bytes = (size_t)d->Cout * 128;
+  const size_t tap_bytes = (size_t)p.Ncta * 128;
   // whole layer resident?  then 3 taps per slab (3 barriers per block), fetched once, multicast over a 4-CTA cluster
   p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
-  if (a_total + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
+  // Weight staging.  Preferred: a 2-deep ring of 3-tap slabs -- with the halo copies that is ~105 KB, so TWO CTAs fit per SM
+  // and programmatic dependent launch really overlaps the next layer's prologue + weight prefetch with this layer's
+  // MMA/epilogue.  (A whole resident layer, 128 KB, multicast over a cluster, serialised the layers: round-1 notes.)
+  const size_t half_sm = 112 * 1024;
+  p.mcast = 0;
+  const bool single_wave = (long long)p.num_tiles * p.nsplit <= (long long)sms;
+  if (single_wave && p.nsplit == 1 && a_total + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
+    // one CTA per SM anyway (e.g. the 128x128 trunk: 128 tiles): whole layer resident, fetched before the dependency
+    // wait and multicast over a 4-CTA cluster -- measured 6.2 us vs 6.9 us for the ring on the 64->64 layer
     p.mcast = 1; p.TPS = 3; p.WST = 3 * p.nblk;
+  } else if (p.nsplit == 1 && 1024 + a_total + 2 * 3 * tap_bytes + 1024 <= half_sm) {
+    // multi-wave grids: 2-deep ring of 3-tap slabs (~105 KB) so TWO CTAs share an SM (256x256: 14.7 us vs 24.0 us)
+    p.TPS = 3; p.WST = 2;
+  } else if (p.nsplit == 1 && a_total + 2 * 3 * tap_bytes <= budget) {
+    p.TPS = 3; p.WST = (int)((budget - a_total) / (3 * tap_bytes));
+    if (p.WST > 3 * p.nblk) p.WST = 3 * p.nblk;
+    if (p.WST > MAX_WST) p.WST = MAX_WST;
   } else {
-    p.mcast = 0; p.TPS = 1;
+    p.TPS = 1;
     int wst = (int)((budget - a_total) / tap_bytes);
     if (wst > 9 * p.nblk) wst = 9 * p.nblk;
     if (wst > MAX_WST) wst = MAX_WST;
@@ -568,9 +633,9 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     p.WST = wst;
   }
   p.w_slab_bytes = (uint32_t)(p.TPS * tap_bytes);
-  p.KS = (p.TPS == 3 && d->mode == 0 && J * 3 * d->Cout <= 512) ? 3 : 1;
+  p.KS = (p.TPS == 3 && d->mode == 0 && J * 3 * p.Ncta <= 512) ? 3 : 1;
   p.CS = (p.mcast && p.num_tiles >= 8) ? 4 : 1;
-  uint32_t cols = (uint32_t)(J * nacc * p.KS * d->Cout), tc = 32;
+  uint32_t cols = (uint32_t)(J * nacc * p.KS * p.Ncta), tc = 32;
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
   const size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float);
@@ -604,7 +669,8 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     return TECO_E_UNSUPPORTED;
   }
   TECO_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
-  const unsigned ctas = (unsigned)((p.num_tiles + p.CS - 1) / p.CS * p.CS);
+  p.tiles_pad = (p.num_tiles + p.CS - 1) / p.CS * p.CS;
+  const unsigned ctas = (unsigned)(p.tiles_pad * p.nsplit);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(NUM_THREADS);

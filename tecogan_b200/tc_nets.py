@@ -1,6 +1,6 @@
 """bf16 tensor-core execution of generator_F / fnet (reference lib/frvsr.py) on the tcgen05 kernel.
 
-Activations are NHWC bf16 with channel counts padded to multiples of 16; weights are re-packed once per
+Activations are NHWC bf16 with channel counts padded to multiples of 64 (one 128-byte swizzled row); weights are re-packed once per
 VariableStore version into the UMMA canonical layout (teco_pack_conv3x3_bf16).  The generator input uses an
 internal channel order  [0,48) = space-to-depth of the warped previous HR frame, [48,51) = LR RGB, [51,64) = 0
 so the fused warp kernel can store 16-byte vectors; the first layer's weights are permuted accordingly.
@@ -39,7 +39,7 @@ _cache = {}
 def _layer(full_name, transpose=False, cin_perm=None, cin_pad=None, f32_out=False):
     """Packed weights for variable scope `full_name` (…/Conv or …/Conv2d_transpose), cached per store version."""
     store = default_store()
-    key = (id(store), store.version, full_name)
+    key = (store.uid, store.version, full_name)
     L = _cache.get(key)
     if L is not None:
         return L
@@ -55,7 +55,7 @@ def _layer(full_name, transpose=False, cin_perm=None, cin_pad=None, f32_out=Fals
     L.cout = cout
     L.wpk = K.packed_weight(w.detach(), L.cin_pad, L.cout_pad, transpose, cin_perm)
     L.bias = K.pad_bias(b.detach(), L.cout_pad) if b is not None else None
-    for k in [k for k in _cache if k[0] == id(store) and k[2] == full_name]:
+    for k in [k for k in _cache if k[0] == store.uid and k[2] == full_name]:
         del _cache[k]
     _cache[key] = L
     return L
@@ -192,10 +192,10 @@ _plans = {}
 
 def _plan(kind, scope, shape, ctor):
     store = default_store()
-    key = (kind, id(store), store.version, scope) + tuple(shape)
+    key = (kind, store.uid, store.version, scope) + tuple(shape)
     p = _plans.get(key)
     if p is None:
-        for k in [k for k in _plans if k[0] == kind and k[1] == id(store) and k[3] == scope and k[4:] == tuple(shape)]:
+        for k in [k for k in _plans if k[0] == kind and k[1] == store.uid and k[3] == scope and k[4:] == tuple(shape)]:
             del _plans[k]
         p = _plans[key] = ctor()
     return p

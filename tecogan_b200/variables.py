@@ -16,8 +16,12 @@ class VariableStore(OrderedDict):
     """name -> fp32 CUDA tensor.  `version` bumps whenever a tensor object is replaced or updated in place
     by an optimiser, so packed bf16 copies (tecogan_b200/lib/ops.py) know when to re-pack."""
 
+    _next_uid = [0]
+
     def __init__(self, device="cuda", seed=1234):
         super().__init__()
+        VariableStore._next_uid[0] += 1
+        self.uid = VariableStore._next_uid[0]      # never reused (id() of a freed store can be): key for packed-weight caches
         self.device = torch.device(device)
         self.gen = torch.Generator().manual_seed(seed)
         self.version = 0
