@@ -293,6 +293,26 @@ def main():
     torch.cuda.synchronize()
     k_us = e0.elapsed_time(e1) * 1000.0 / (5 * reps)
 
+    # --- HBM-bound kernel of the path: fused upscale_four + warp + space-to-depth feedback, on a batch larger than L2
+    # (32 clips of 256x256 LR -> 1024x1024 HR: 403 MB read + 201 MB written), algorithmic 18.5 B per HR pixel
+    wn, wh = 32, 256
+    w_pre = torch.rand(wn, 4 * wh, 4 * wh, 3, device="cuda")
+    yy, xx = torch.meshgrid(torch.linspace(0, 6.28, wh, device="cuda"), torch.linspace(0, 6.28, wh, device="cuda"), indexing="ij")
+    w_flow = torch.stack((1.5 + 0.5 * torch.sin(yy + xx), -0.75 + 0.5 * torch.cos(yy - xx)), dim=-1).expand(wn, wh, wh, 2).contiguous()
+    w_dst = torch.zeros(wn, wh, wh, 64, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        K.warp_s2d_fused(w_pre, w_flow, w_dst, 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        K.warp_s2d_fused(w_pre, w_flow, w_dst, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    warp_us = e0.elapsed_time(e1) * 1000.0 / 5
+    warp_bytes = wn * (4 * wh) * (4 * wh) * 18.5
+    del w_pre, w_flow, w_dst
+
     t = torch.tensor([ms_res, ms_e2e], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -310,6 +330,13 @@ def main():
         peak_tf = float(peaks.get("bf16_tflops", 1590.0))
         peak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s"
         ach_tf = RESBLOCK_CONV_FLOP / (k_us * 1e-6) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")))["traffic_bytes_per_launch"]
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        warp_gbs = warp_bytes / (warp_us * 1e-6) / 1e9
         graph_launches = eng.launches_per_frame
         line = {
             "metric": "HR frames/sec (4x SR)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -327,11 +354,16 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (3x3 64->64 @128x128, res-block layer)",
                          "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                          "peak_source": peak_src, "us_per_launch": k_us, "flop_per_launch": RESBLOCK_CONV_FLOP,
-                         "traffic": None,
+                         "traffic": traffic,
                          "whole_frame": {"algorithmic_gflop_per_frame": 2e-9 * MACS_PER_LR_PX * LR_H * LR_W,
                                          "achieved_tflops": 2e-12 * MACS_PER_LR_PX * LR_H * LR_W * value / world,
                                          "frac_of_sustained": 2e-12 * MACS_PER_LR_PX * LR_H * LR_W * value / world
                                          / float(peaks.get("bf16_tflops_sustained", 1400.0))}},
+            "roofline_hbm": {"bound": "hbm", "kernel": "warp_s2d_fused_kernel (upscale_four + dense_image_warp + space_to_depth), "
+                                                         "32 x 1024x1024 HR frames, smooth motion field (translation + low-frequency), working set 604 MB > L2",
+                             "achieved": warp_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": warp_gbs / peak_gbs,
+                             "us_per_launch": warp_us, "algorithmic_bytes_per_launch": warp_bytes,
+                             "peak_source": "measured copy (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
             "wall_s_resident_leg": wall, "python_abi_calls_in_timed_region": eager_calls,
         }
         if world == 1 and not args.no_cpu_baseline:

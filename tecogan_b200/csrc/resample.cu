@@ -95,87 +95,166 @@ __global__ void warp_bwd_f32_kernel(const float* __restrict__ img, const float* 
 }
 
 // ---- fused feedback: flow_lr -> (symmetric pad, x4, upscale_four) -> warp(pre_gen) -> s2d into dst.
-// One thread per (n, ly, lx, dy): 4 HR pixels x 3 channels = 12 contiguous destination values.
+// CTA tile = 2 LR rows x 32 LR columns (8 x 128 HR pixels); one thread per (LR pixel, dy): 4 HR pixels x 3 channels
+// = 12 contiguous destination values.  The HR flow inside the tile is a convex combination of the 3 x 33 LR flow
+// samples around it, so their min/max bound every query of the tile: the CTA stages that source window of the
+// previous HR frame in shared memory with fully coalesced loads and gathers from there (round-1 ncu: the direct
+// per-thread gather moved 30 sectors per request through L1, 31x the unique bytes).  Windows that do not fit
+// (|flow| spread > ~40 px inside one tile) take the direct global gather path.
+constexpr int WS_TLH = 2, WS_TLW = 32;                 // LR tile
+constexpr int WS_SMEM_FLOATS = 6 * 1024;               // 24 KB window budget: up to ~14 x 146 source pixels, 8 CTAs / SM
+
+struct FlowQ { float2 f00, f01, f10, f11; };
+
+__device__ __forceinline__ FlowQ load_flow_quad(const float* __restrict__ fb, int ly, int lx, int h, int w, int fh, int fw) {
+  // flow_lr neighbours (upscale_four pads bottom/right by replication AFTER the symmetric pad of main.py:212)
+  int i0 = ly, i1 = min(ly + 1, h - 1), j0 = lx, j1 = min(lx + 1, w - 1);
+  int si0 = i0 < fh ? i0 : 2 * fh - 1 - i0, si1 = i1 < fh ? i1 : 2 * fh - 1 - i1;
+  int sj0 = j0 < fw ? j0 : 2 * fw - 1 - j0, sj1 = j1 < fw ? j1 : 2 * fw - 1 - j1;
+  FlowQ q;
+  q.f00 = *reinterpret_cast<const float2*>(fb + ((long long)si0 * fw + sj0) * 2);
+  q.f01 = *reinterpret_cast<const float2*>(fb + ((long long)si0 * fw + sj1) * 2);
+  q.f10 = *reinterpret_cast<const float2*>(fb + ((long long)si1 * fw + sj0) * 2);
+  q.f11 = *reinterpret_cast<const float2*>(fb + ((long long)si1 * fw + sj1) * 2);
+  q.f00.x *= 4.f; q.f00.y *= 4.f; q.f01.x *= 4.f; q.f01.y *= 4.f;
+  q.f10.x *= 4.f; q.f10.y *= 4.f; q.f11.x *= 4.f; q.f11.y *= 4.f;
+  return q;
+}
+
 template <bool kBf16>
 __global__ void __launch_bounds__(TPB)
 warp_s2d_fused_kernel(const float* __restrict__ pre_gen, const float* __restrict__ flow_lr, void* __restrict__ dst,
                       float* __restrict__ warped_out, int N, int h, int w, int fh, int fw, int dst_cpitch, int ch_off,
-                      float in_scale, float in_shift) {
+                      float in_scale, float in_shift, int tiles_x, int tiles_y) {
+  extern __shared__ float win[];
+  __shared__ float red[4][8];
+  __shared__ int s_win[5];   // y_lo, x_lo, rows, cols, use_smem
   const int H = 4 * h, W = 4 * w;
-  long long total = (long long)N * h * w * 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int dy = (int)(i & 3);
-    long long t = i >> 2;
-    int lx = (int)(t % w);
-    t /= w;
-    int ly = (int)(t % h);
-    int n = (int)(t / h);
-    // flow_lr neighbours (upscale_four pads bottom/right by replication AFTER the symmetric pad)
-    int i0 = ly, i1 = min(ly + 1, h - 1), j0 = lx, j1 = min(lx + 1, w - 1);
-    int si0 = i0 < fh ? i0 : 2 * fh - 1 - i0, si1 = i1 < fh ? i1 : 2 * fh - 1 - i1;
-    int sj0 = j0 < fw ? j0 : 2 * fw - 1 - j0, sj1 = j1 < fw ? j1 : 2 * fw - 1 - j1;
-    const float* fb = flow_lr + (long long)n * fh * fw * 2;
-    float2 f00 = *reinterpret_cast<const float2*>(fb + ((long long)si0 * fw + sj0) * 2);
-    float2 f01 = *reinterpret_cast<const float2*>(fb + ((long long)si0 * fw + sj1) * 2);
-    float2 f10 = *reinterpret_cast<const float2*>(fb + ((long long)si1 * fw + sj0) * 2);
-    float2 f11 = *reinterpret_cast<const float2*>(fb + ((long long)si1 * fw + sj1) * 2);
-    f00.x *= 4.f; f00.y *= 4.f; f01.x *= 4.f; f01.y *= 4.f;
-    f10.x *= 4.f; f10.y *= 4.f; f11.x *= 4.f; f11.y *= 4.f;
-    float wy1 = 0.25f * dy, wy0 = 1.f - wy1;
-    int Y = 4 * ly + dy;
-    float vals[12];
-    const float* img = pre_gen + (long long)n * H * W * 3;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int n = tile / tiles_y;
+  const int ly0 = ty * WS_TLH, lx0 = tx * WS_TLW;
+  const float* fb = flow_lr + (long long)n * fh * fw * 2;
+  const float* img = pre_gen + (long long)n * H * W * 3;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  // ---- bound the flow over the tile: samples (ly0..ly0+2) x (lx0..lx0+32), clamped like upscale_four
+  float mny = 1e30f, mxy = -1e30f, mnx = 1e30f, mxx = -1e30f;
+  if (tid < (WS_TLH + 1) * (WS_TLW + 1)) {
+    int i = min(ly0 + tid / (WS_TLW + 1), h - 1), j = min(lx0 + tid % (WS_TLW + 1), w - 1);
+    int si = i < fh ? i : 2 * fh - 1 - i, sj = j < fw ? j : 2 * fw - 1 - j;
+    float2 f = *reinterpret_cast<const float2*>(fb + ((long long)si * fw + sj) * 2);
+    mny = mxy = f.x * 4.f;
+    mnx = mxx = f.y * 4.f;
+  }
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx) {
-      float wx1 = 0.25f * dx, wx0 = 1.f - wx1;
-      float fy = f00.x * wy0 * wx0 + f01.x * wy0 * wx1 + f10.x * wy1 * wx0 + f11.x * wy1 * wx1;
-      float fx = f00.y * wy0 * wx0 + f01.y * wy0 * wx1 + f10.y * wy1 * wx0 + f11.y * wy1 * wx1;
-      int X = 4 * lx + dx;
-      Bil b = bil_setup((float)Y - fy, (float)X - fx, H, W);
-      const float* p00 = img + ((long long)b.y0 * W + b.x0) * 3;
-      const float* p10 = p00 + (long long)W * 3;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float tl = p00[c], tr = p00[3 + c], bl = p10[c], br = p10[3 + c];
-        float top = b.ax * (tr - tl) + tl;
-        float bot = b.ax * (br - bl) + bl;
-        vals[dx * 3 + c] = b.ay * (bot - top) + top;
+  for (int o = 16; o > 0; o >>= 1) {
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+  }
+  if (lane == 0) { red[0][wid] = mny; red[1][wid] = mxy; red[2][wid] = mnx; red[3][wid] = mxx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < TPB / 32; ++k) {
+      mny = fminf(mny, red[0][k]); mxy = fmaxf(mxy, red[1][k]);
+      mnx = fminf(mnx, red[2][k]); mxx = fmaxf(mxx, red[3][k]);
+    }
+    const int Y0 = 4 * ly0, X0 = 4 * lx0;
+    // queries: Y - fy in [Y0 - mxy, Y0 + 7 - mny]; floor clamped to [0, H-2], plus the +1 neighbour row
+    int y_lo = (int)fminf(fmaxf(floorf((float)Y0 - mxy) - 1.f, 0.f), (float)(H - 2));
+    int y_hi = (int)fminf(fmaxf(floorf((float)(Y0 + 4 * WS_TLH - 1) - mny) + 1.f, 0.f), (float)(H - 2)) + 1;
+    int x_lo = (int)fminf(fmaxf(floorf((float)X0 - mxx) - 1.f, 0.f), (float)(W - 2));
+    int x_hi = (int)fminf(fmaxf(floorf((float)(X0 + 4 * WS_TLW - 1) - mnx) + 1.f, 0.f), (float)(W - 2)) + 1;
+    int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
+    s_win[0] = y_lo; s_win[1] = x_lo; s_win[2] = rows; s_win[3] = cols;
+    // stage only when the window is compact (<= 2.5x the tile's own 8x128 pixels): rough flow fields would re-read more
+    // through the window than the direct L1 gather does
+    s_win[4] = ((long long)rows * cols * 3 <= WS_SMEM_FLOATS && (long long)rows * cols * 2 <= 5LL * (4 * WS_TLH) * (4 * WS_TLW)) ? 1 : 0;
+  }
+  __syncthreads();
+  const int y_lo = s_win[0], x_lo = s_win[1], rows = s_win[2], cols = s_win[3];
+  const bool use_smem = s_win[4] != 0;
+  const int rowf = cols * 3;
+  if (use_smem) {   // coalesced row copies of the window
+    for (int r = wid; r < rows; r += TPB / 32) {
+      const float* src = img + ((long long)(y_lo + r) * W + x_lo) * 3;
+      float* d = win + r * rowf;
+      int k = lane;
+      for (; k + 96 < rowf; k += 128) {          // four independent 128-byte warp loads in flight
+        float a0 = src[k], a1 = src[k + 32], a2 = src[k + 64], a3 = src[k + 96];
+        d[k] = a0; d[k + 32] = a1; d[k + 64] = a2; d[k + 96] = a3;
       }
+      for (; k < rowf; k += 32) d[k] = src[k];
     }
-    if (warped_out) {
-      float* wo = warped_out + (((long long)n * H + Y) * W + 4 * lx) * 3;
+  }
+  __syncthreads();
+
+  const int dy = tid & 3, lxl = (tid >> 2) & (WS_TLW - 1), lyl = tid >> 7;
+  const int ly = ly0 + lyl, lx = lx0 + lxl;
+  if (ly >= h || lx >= w) return;
+  const FlowQ q = load_flow_quad(fb, ly, lx, h, w, fh, fw);
+  const float wy1 = 0.25f * dy, wy0 = 1.f - wy1;
+  const int Y = 4 * ly + dy;
+  float vals[12];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) wo[k] = vals[k];
+  for (int dx = 0; dx < 4; ++dx) {
+    float wx1 = 0.25f * dx, wx0 = 1.f - wx1;
+    float fy = q.f00.x * wy0 * wx0 + q.f01.x * wy0 * wx1 + q.f10.x * wy1 * wx0 + q.f11.x * wy1 * wx1;
+    float fx = q.f00.y * wy0 * wx0 + q.f01.y * wy0 * wx1 + q.f10.y * wy1 * wx0 + q.f11.y * wy1 * wx1;
+    int X = 4 * lx + dx;
+    Bil b = bil_setup((float)Y - fy, (float)X - fx, H, W);
+    const float *p00, *p10;
+    if (use_smem) {
+      p00 = win + (b.y0 - y_lo) * rowf + (b.x0 - x_lo) * 3;
+      p10 = p00 + rowf;
+    } else {
+      p00 = img + ((long long)b.y0 * W + b.x0) * 3;
+      p10 = p00 + (long long)W * 3;
     }
-    long long o = (((long long)n * h + ly) * w + lx) * dst_cpitch + ch_off + dy * 12;
-    if (kBf16) {
-      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst) + o;
-      if ((o & 3) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          __nv_bfloat162 a = __floats2bfloat162_rn(vals[4 * k] * in_scale + in_shift, vals[4 * k + 1] * in_scale + in_shift);
-          __nv_bfloat162 c = __floats2bfloat162_rn(vals[4 * k + 2] * in_scale + in_shift, vals[4 * k + 3] * in_scale + in_shift);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&a);
-          u.y = *reinterpret_cast<uint32_t*>(&c);
-          *reinterpret_cast<uint2*>(d + 4 * k) = u;
-        }
-      } else {
+    for (int c = 0; c < 3; ++c) {
+      float tl = p00[c], tr = p00[3 + c], bl = p10[c], br = p10[3 + c];
+      float top = b.ax * (tr - tl) + tl;
+      float bot = b.ax * (br - bl) + bl;
+      vals[dx * 3 + c] = b.ay * (bot - top) + top;
+    }
+  }
+  if (warped_out) {
+    float* wo = warped_out + (((long long)n * H + Y) * W + 4 * lx) * 3;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) d[k] = __float2bfloat16_rn(vals[k] * in_scale + in_shift);
+    for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(wo + 4 * k) = make_float4(vals[4 * k], vals[4 * k + 1], vals[4 * k + 2], vals[4 * k + 3]);
+  }
+  long long o = (((long long)n * h + ly) * w + lx) * dst_cpitch + ch_off + dy * 12;
+  if (kBf16) {
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst) + o;
+    if ((o & 3) == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(vals[4 * k] * in_scale + in_shift, vals[4 * k + 1] * in_scale + in_shift);
+        __nv_bfloat162 c = __floats2bfloat162_rn(vals[4 * k + 2] * in_scale + in_shift, vals[4 * k + 3] * in_scale + in_shift);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&c);
+        *reinterpret_cast<uint2*>(d + 4 * k) = u;
       }
     } else {
-      float* d = reinterpret_cast<float*>(dst) + o;
-      if ((o & 3) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-          *reinterpret_cast<float4*>(d + 4 * k) =
-              make_float4(vals[4 * k] * in_scale + in_shift, vals[4 * k + 1] * in_scale + in_shift,
-                          vals[4 * k + 2] * in_scale + in_shift, vals[4 * k + 3] * in_scale + in_shift);
-      } else {
+      for (int k = 0; k < 12; ++k) d[k] = __float2bfloat16_rn(vals[k] * in_scale + in_shift);
+    }
+  } else {
+    float* d = reinterpret_cast<float*>(dst) + o;
+    if ((o & 3) == 0) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) d[k] = vals[k] * in_scale + in_shift;
-      }
+      for (int k = 0; k < 3; ++k)
+        *reinterpret_cast<float4*>(d + 4 * k) =
+            make_float4(vals[4 * k] * in_scale + in_shift, vals[4 * k + 1] * in_scale + in_shift,
+                        vals[4 * k + 2] * in_scale + in_shift, vals[4 * k + 3] * in_scale + in_shift);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) d[k] = vals[k] * in_scale + in_shift;
     }
   }
 }
@@ -473,14 +552,25 @@ int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, f
                  "teco_warp_s2d_fused: bad shape h=%d w=%d fh=%d fw=%d", h, w, fh, fw);
   TECO_CHECK_ARG(ch_off >= 0 && ch_off + 48 <= dst_cpitch, "teco_warp_s2d_fused: 48 channels do not fit at ch_off=%d in pitch %d",
                  ch_off, dst_cpitch);
-  long long total = (long long)N * h * w * 4;
-  if (dst_bf16) {
-    LAUNCH1D(warp_s2d_fused_kernel<true>, total, pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw, dst_cpitch, ch_off,
-             in_scale, in_shift);
-  } else {
-    LAUNCH1D(warp_s2d_fused_kernel<false>, total, pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw, dst_cpitch, ch_off,
-             in_scale, in_shift);
+  const int tiles_x = teco_ceil_div(w, WS_TLW), tiles_y = teco_ceil_div(h, WS_TLH);
+  const long long ctas = (long long)N * tiles_x * tiles_y;
+  TECO_CHECK_ARG(ctas < (1LL << 31), "teco_warp_s2d_fused: too many tiles");
+  const size_t smem = WS_SMEM_FLOATS * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    TECO_CUDA_CALL(cudaFuncSetAttribute(warp_s2d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TECO_CUDA_CALL(cudaFuncSetAttribute(warp_s2d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
   }
+  // the 4-float stores of warped_out need 16-byte alignment of every (row, 4*lx) start: W*3 floats per row, 4*lx*3 = 12 lx
+  TECO_CHECK_ARG(!warped_out || ((((uintptr_t)warped_out) & 15) == 0), "teco_warp_s2d_fused: warped_out must be 16-byte aligned");
+  if (dst_bf16)
+    warp_s2d_fused_kernel<true><<<(unsigned)ctas, TPB, smem, (cudaStream_t)stream>>>(pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw,
+                                                                                 dst_cpitch, ch_off, in_scale, in_shift, tiles_x, tiles_y);
+  else
+    warp_s2d_fused_kernel<false><<<(unsigned)ctas, TPB, smem, (cudaStream_t)stream>>>(pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw,
+                                                                                  dst_cpitch, ch_off, in_scale, in_shift, tiles_x, tiles_y);
+  TECO_CUDA_LAUNCH_CHECK("teco_warp_s2d_fused");
   return TECO_OK;
 }
 

@@ -55,14 +55,18 @@ def conv_case(n, h, w, cin, cout, mode=0, graph=True):
           % (mode, n, h, w, cin, cout, us, tf, tf / PEAK_TF, "graph" if graph else "eager"), flush=True)
 
 
-def warp_case(n, h, w):
+def warp_case(n, h, w, rough=False):
     pre = torch.rand(n, 4 * h, 4 * w, 3, device="cuda")
-    flow = torch.randn(n, h, w, 2, device="cuda")
+    if rough:    # white-noise flow, +-12 HR px inside one tile: nothing like a motion field, the direct-gather path
+        flow = torch.randn(n, h, w, 2, device="cuda")
+    else:        # smooth motion: global translation (1.5, -0.75) LR px plus a low-frequency component
+        yy, xx = torch.meshgrid(torch.linspace(0, 6.28, h, device="cuda"), torch.linspace(0, 6.28, w, device="cuda"), indexing="ij")
+        flow = torch.stack((1.5 + 0.5 * torch.sin(yy + xx), -0.75 + 0.5 * torch.cos(yy - xx)), dim=-1).expand(n, h, w, 2).contiguous()
     dst = torch.zeros(n, h, w, 64, device="cuda", dtype=torch.bfloat16)
     us = time_us(lambda: K.warp_s2d_fused(pre, flow, dst, 0))
     byts = n * 16 * h * w * (12 + 6) + n * h * w * 8
-    print("warp_s2d_fused N=%d LR %dx%d: %.2f us  %.0f GB/s algorithmic  %.3f of measured HBM peak"
-          % (n, h, w, us, byts / us / 1e3, byts / us / 1e3 / PEAK_GBS), flush=True)
+    print("warp_s2d_fused N=%d LR %dx%d (%s flow): %.2f us  %.0f GB/s algorithmic  %.3f of measured HBM peak"
+          % (n, h, w, "rough" if rough else "smooth", us, byts / us / 1e3, byts / us / 1e3 / PEAK_GBS), flush=True)
 
 
 if __name__ == "__main__":
@@ -81,6 +85,7 @@ if __name__ == "__main__":
         warp_case(1, 128, 128)
         warp_case(8, 256, 256)
         warp_case(32, 256, 256)
+        warp_case(32, 256, 256, rough=True)
     if which == "one":   # for ncu: a handful of launches of the dominant layer
         x = torch.randn(1, 128, 128, 64, device="cuda").to(torch.bfloat16)
         wpk = K.packed_weight(torch.randn(3, 3, 64, 64, device="cuda") * 0.05, 64, 64)
