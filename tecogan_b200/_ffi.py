@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libteco.so")
+LIB_PATH = os.environ.get("TECO_LIB", os.path.join(_HERE, "libteco.so"))   # TECO_LIB: A/B-test another build of the same ABI
 
 ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_TANH24, ACT_SIGMOID = 0, 1, 2, 3, 4
 

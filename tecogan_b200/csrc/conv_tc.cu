@@ -40,7 +40,8 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct TcParams {
   int N, H, W, Cin, Cout;             // Cout = channel pitch of y / res / bias (all output channels)
-  int Ncta, nsplit, tiles_pad;        // output channels per CTA (UMMA N), Cout splits, tile count padded to the cluster size
+  int Ncta, nsplit, G, AS;            // output channels per CTA (UMMA N), Cout splits, CTAs per split (persistent: each
+                                      // walks tiles c, c+G, ...), TMEM accumulator stages (1 or 2)
   int tiles_x, tiles_y, J;
   int mode, act, out_f32_c;
   float post_scale, post_shift;
@@ -170,6 +171,10 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // MODE 0 conv / 1 transposed conv; TPS taps per weight slab; J sub-tiles per CTA; KS K-split accumulator chains.
 // They are compile-time so that the MMA issue loop is a fully unrolled stream of UTCHMMA whose descriptors differ
 // from per-stage bases by immediates (uniform-datapath adds, no per-instruction R2UR).
+//
+// Persistent and pipelined: a CTA walks tiles c, c+G, c+2G, ... of its Cout split.  The halo ring (HST stages), the
+// weight ring (or the resident layer, loaded once) and AS TMEM accumulator stages let the TMA producer, the MMA
+// issuer and the epilogue warps work on three different tiles at the same time.
 template <int MODE, int TPS, int J, int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
@@ -180,24 +185,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint8_t* halo_base = smem;                                             // HST stages x 3 kx-copies
   uint8_t* w_base = smem + (size_t)p.HST * p.halo_stage_bytes;           // WST weight slabs
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)p.WST * p.w_slab_bytes);
-  uint64_t* halo_full = bars;
-  uint64_t* halo_empty = bars + 2;
-  uint64_t* w_full = bars + 4;
-  uint64_t* w_empty = bars + 4 + MAX_WST;
-  uint64_t* acc_full = bars + 4 + 2 * MAX_WST;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * MAX_WST + 1);
-  float* s_bias = reinterpret_cast<float*>(bars + 4 + 2 * MAX_WST + 2);   // [Cout]
+  uint64_t* halo_full = bars;                    // [2]
+  uint64_t* halo_empty = bars + 2;               // [2]
+  uint64_t* w_full = bars + 4;                   // [MAX_WST]
+  uint64_t* w_empty = bars + 4 + MAX_WST;        // [MAX_WST]
+  uint64_t* acc_full = bars + 4 + 2 * MAX_WST;   // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(acc_empty + 3);   // [Ncta]
 
-  // tile coordinates
-  int tile = blockIdx.x % p.tiles_pad;      // grid = nsplit x (tiles padded to a multiple of the cluster size)
-  const int n0 = (blockIdx.x / p.tiles_pad) * p.Ncta;   // first output channel of this CTA (all CTAs of a cluster share it)
-  const bool active = tile < p.num_tiles;
-  if (!active) tile = 0;
-  const int tx = tile % p.tiles_x;
-  tile /= p.tiles_x;
-  const int ty = tile % p.tiles_y;
-  const int n = tile / p.tiles_y;
-  const int x0 = tx * 8 * J, y0 = ty * TILE_ROWS;
+  // work assignment: grid = nsplit x G CTAs; CTA c of a split owns tiles c, c+G, ...
+  const int c_in_split = blockIdx.x % p.G;
+  const int n0 = (blockIdx.x / p.G) * p.Ncta;   // first output channel of this CTA (all CTAs of a cluster share it)
+  const int my_tiles = c_in_split < p.num_tiles ? (p.num_tiles - c_in_split + p.G - 1) / p.G : 0;
   long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
 #define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   if (threadIdx.x == 0) STAMP(0);
@@ -211,7 +211,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       mbar_init(smem_u32(&w_full[i]), 1);
       mbar_init(smem_u32(&w_empty[i]), 1);
     }
-    mbar_init(smem_u32(acc_full), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), NUM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -234,15 +237,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   constexpr int slabs_per_blk = 9 / TPS;
   constexpr int row_bytes = 8 * J * 128;         // one box row (8J pixels x 128 B)
   constexpr uint32_t copy_bytes = (uint32_t)(HALO_ROWS * row_bytes);
+  const int slabs_per_tile = slabs_per_blk * p.nblk;
+  const uint32_t acc_stage_cols = (uint32_t)(J * nacc * KS * p.Ncta);   // TMEM columns of one accumulator stage
+
+  auto tile_coords = [&](int it, int& n, int& y0, int& x0) {
+    int tile = c_in_split + it * p.G;
+    const int tx = tile % p.tiles_x;
+    tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y;
+    n = tile / p.tiles_y;
+    x0 = tx * 8 * J;
+    y0 = ty * TILE_ROWS;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     // Issue cost of one bulk/tensor copy is a few hundred cycles, so independent copies are issued by different lanes.
     if (p.mcast) {
-      // Weights do not depend on the previous layer: fetch them before the dependency wait.  Each CTA of the
-      // cluster fetches 1/CS of every slab and multicasts it to all CS CTAs (one L2 read per cluster).
+      // Resident weights (whole layer fits): they do not depend on the previous layer -> fetch them once, before the
+      // dependency wait.  With CS > 1 each CTA of the cluster fetches 1/CS of every slab and multicasts it.
       const int sidx = lane;
-      if (sidx < slabs_per_blk * p.nblk) {
+      if (sidx < slabs_per_tile) {
         const uint32_t crank = p.CS > 1 ? cluster_ctarank() : 0;
         const uint32_t part = p.w_slab_bytes / (uint32_t)p.CS;
         const uint16_t mask = (uint16_t)((1u << p.CS) - 1u);
@@ -256,23 +271,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
       __syncwarp();
     }
-    // Ring mode: the first WST weight slabs do not depend on the previous layer either -> issue them before the wait.
-    const int total_slabs = slabs_per_blk * p.nblk;
+    // Ring mode: slab sequence q = 0 .. my_tiles*slabs_per_tile-1 through WST stages; the first WST do not depend on
+    // the previous layer either -> issue them before the wait.
+    const int total_slabs = my_tiles * slabs_per_tile;
     int next_slab = 0;
-    if (!p.mcast && lane == 0) {
-      for (; next_slab < total_slabs && next_slab < p.WST; ++next_slab) {
-        const int b = next_slab / slabs_per_blk, g = next_slab - slabs_per_blk * b;
-        mbar_expect_tx(smem_u32(&w_full[next_slab]), p.w_slab_bytes);
-        const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout + n0) * 128;
-        bulk_load_1d(smem_u32(w_base + (size_t)next_slab * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[next_slab]));
-      }
-    }
+    auto issue_slab = [&](int q) {
+      const int st = q % p.WST, use = q / p.WST, sl = q % slabs_per_tile;
+      const int b = sl / slabs_per_blk, g = sl - slabs_per_blk * b;
+      if (use > 0) mbar_wait(smem_u32(&w_empty[st]), (uint32_t)((use - 1) & 1));   // MMAs of the previous use have retired
+      mbar_expect_tx(smem_u32(&w_full[st]), p.w_slab_bytes);
+      const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout + n0) * 128;
+      bulk_load_1d(smem_u32(w_base + (size_t)st * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[st]));
+    };
+    if (!p.mcast && lane == 0)
+      for (; next_slab < total_slabs && next_slab < p.WST; ++next_slab) issue_slab(next_slab);
     if (lane == 0) STAMP(9);
     pdl_wait();   // the previous kernel's output (our input x) is complete and visible from here on
     if (lane == 0) STAMP(10);
-    if (active) {
-      int hs = 0;
-      uint32_t hph = 0;
+    int hs = 0;
+    uint32_t hph = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      int n, y0, x0;
+      tile_coords(it, n, y0, x0);
       for (int b = 0; b < p.nblk; ++b) {
         if (lane == 0) {
           mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
@@ -282,105 +302,110 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (lane < ncopies)
           tma_load_4d(smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes + (size_t)lane * copy_bytes), &tmap,
                       smem_u32(&halo_full[hs]), b * CB, x0 - 1 + lane, y0 - 1, n);
-        if (!p.mcast && lane == 0) {
-          for (; next_slab < (b + 1) * slabs_per_blk; ++next_slab) {   // slabs of this block not yet in flight
-            const int st = next_slab % p.WST, use = next_slab / p.WST;
-            const int g = next_slab - slabs_per_blk * b;
-            mbar_wait(smem_u32(&w_empty[st]), (uint32_t)((use - 1) & 1));   // the MMAs of the previous use have retired
-            mbar_expect_tx(smem_u32(&w_full[st]), p.w_slab_bytes);
-            const uint8_t* src = p.wpk + ((size_t)(b * 9 + g * TPS) * p.Cout + n0) * 128;
-            bulk_load_1d(smem_u32(w_base + (size_t)st * p.w_slab_bytes), src, p.w_slab_bytes, smem_u32(&w_full[st]));
-          }
-        }
+        if (!p.mcast && lane == 0)   // slabs up to the end of this block that are not in flight yet
+          for (; next_slab < it * slabs_per_tile + (b + 1) * slabs_per_blk; ++next_slab) issue_slab(next_slab);
         __syncwarp();
         if (++hs == p.HST) { hs = 0; hph ^= 1; }
       }
-    } else if (p.mcast && lane == 0) {
+    }
+    if (my_tiles == 0 && p.mcast && lane == 0) {
       // padding CTA of a cluster: it only relays its share of the weights; stay until they have landed here too
-      for (int sidx = 0; sidx < slabs_per_blk * p.nblk; ++sidx) mbar_wait(smem_u32(&w_full[sidx]), 0);
+      for (int sidx = 0; sidx < slabs_per_tile; ++sidx) mbar_wait(smem_u32(&w_full[sidx]), 0);
     }
     __syncwarp();
-  } else if (warp == 1 && active) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = umma_idesc(p.Ncta);
     constexpr uint32_t a_sbo = (uint32_t)row_bytes;   // next 8-pixel group of the M=128 sub-tile = next image row
     constexpr uint32_t b_sbo = 1024u;                 // next 8 output channels
     int hs = 0, ws = 0;
     uint32_t hph = 0, wph = 0;
-    uint32_t started = 0;  // bit (j*nacc+phase): accumulator already written once
-    for (int b = 0; b < p.nblk; ++b) {
-      mbar_wait_warp(smem_u32(&halo_full[hs]), hph);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int as = (p.AS == 2) ? (it & 1) : 0;
+      const uint32_t ause = (uint32_t)((p.AS == 2) ? (it >> 1) : it);
+      mbar_wait_warp(smem_u32(&acc_empty[as]), (ause & 1u) ^ 1u);   // the epilogue has drained this accumulator stage
       tcgen05_fence_after();
-      if (lane == 0 && b == 0) STAMP(2);
-      const uint32_t halo_addr = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
-      for (int g = 0; g < slabs_per_blk; ++g) {
-        mbar_wait_warp(smem_u32(&w_full[ws]), wph);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)as * acc_stage_cols;
+      uint32_t started = 0;  // bit (j*nacc+phase): accumulator already written once (for this tile)
+      for (int b = 0; b < p.nblk; ++b) {
+        mbar_wait_warp(smem_u32(&halo_full[hs]), hph);
         tcgen05_fence_after();
-        if (lane == 0 && b == 0) STAMP(16 + g);
-        {
-          // Whole (converged) warp computes the warp-uniform bases; one elected lane issues the unrolled MMA stream.
-          const uint32_t slab_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
-          const uint64_t a_base = umma_desc_sw128(halo_addr, a_sbo);
-          const uint64_t b_base = umma_desc_sw128(slab_addr, b_sbo);
-          const uint32_t tap_stride16 = (uint32_t)(p.Ncta * 128) >> 4;   // weight bytes per tap, in descriptor units
-          // per-tap row/copy/phase (TPS == 3: ky = g, kx = tt; TPS == 1: tap = g)
-          uint32_t a_off16[TPS], acc_idx[TPS];
-#pragma unroll
-          for (int tt = 0; tt < TPS; ++tt) {
-            const int t = g * TPS + tt;
-            const int ky = (TPS == 3) ? g : t / 3, kx = (TPS == 3) ? tt : t - 3 * (t / 3);
-            int ry, rx, phase;
-            if (MODE == 1) {  // transposed conv: tap -> (input offset, output phase)
-              ry = (ky == 2) ? 0 : 1;
-              rx = (kx == 2) ? 0 : 1;
-              phase = ((ky == 1) ? 2 : 0) + ((kx == 1) ? 1 : 0);
-            } else {
-              ry = ky; rx = kx; phase = 0;
-            }
-            a_off16[tt] = ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
-            acc_idx[tt] = (uint32_t)(phase * KS + (KS > 1 ? tt : 0));
+        if (lane == 0 && b == 0 && it == 0) STAMP(2);
+        const uint32_t halo_addr = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
+        for (int g = 0; g < slabs_per_blk; ++g) {
+          if (p.mcast) {   // resident: slab index is fixed, the barrier completes exactly once
+            ws = b * slabs_per_blk + g;
+            if (it == 0) mbar_wait_warp(smem_u32(&w_full[ws]), 0);
+          } else {
+            mbar_wait_warp(smem_u32(&w_full[ws]), wph);
           }
-          const uint32_t started_now = started;
-          if (elect_one()) {
-            // order: sub-tile, k-step, tap -> consecutive MMAs hit different accumulators when KS > 1 / MODE == 1
+          tcgen05_fence_after();
+          if (lane == 0 && b == 0 && it == 0) STAMP(16 + g);
+          {
+            // Whole (converged) warp computes the warp-uniform bases; one elected lane issues the unrolled MMA stream.
+            const uint32_t slab_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
+            const uint64_t a_base = umma_desc_sw128(halo_addr, a_sbo);
+            const uint64_t b_base = umma_desc_sw128(slab_addr, b_sbo);
+            const uint32_t tap_stride16 = (uint32_t)(p.Ncta * 128) >> 4;   // weight bytes per tap, in descriptor units
+            // per-tap row/copy/phase (TPS == 3: ky = g, kx = tt; TPS == 1: tap = g)
+            uint32_t a_off16[TPS], acc_idx[TPS];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
+            for (int tt = 0; tt < TPS; ++tt) {
+              const int t = g * TPS + tt;
+              const int ky = (TPS == 3) ? g : t / 3, kx = (TPS == 3) ? tt : t - 3 * (t / 3);
+              int ry, rx, phase;
+              if (MODE == 1) {  // transposed conv: tap -> (input offset, output phase)
+                ry = (ky == 2) ? 0 : 1;
+                rx = (kx == 2) ? 0 : 1;
+                phase = ((ky == 1) ? 2 : 0) + ((kx == 1) ? 1 : 0);
+              } else {
+                ry = ky; rx = kx; phase = 0;
+              }
+              a_off16[tt] = ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
+              acc_idx[tt] = (uint32_t)(phase * KS + (KS > 1 ? tt : 0));
+            }
+            const uint32_t started_now = started;
+            if (elect_one()) {
+              // order: sub-tile, k-step, tap -> consecutive MMAs hit different accumulators when KS > 1 / MODE == 1
 #pragma unroll
-              for (int s = 0; s < CB / 16; ++s) {
+              for (int j = 0; j < J; ++j) {
 #pragma unroll
-                for (int tt = 0; tt < TPS; ++tt) {
-                  const uint32_t acc = (uint32_t)(j * nacc * KS) + acc_idx[tt];
-                  uint32_t accum = 1u;
-                  if (s == 0) {   // first k-step of this slab: overwrite only if nobody has written this accumulator yet
-                    accum = (started_now >> acc) & 1u;
+                for (int s = 0; s < CB / 16; ++s) {
 #pragma unroll
-                    for (int t2 = 0; t2 < tt; ++t2) accum |= (acc_idx[t2] == acc_idx[tt]) ? 1u : 0u;
+                  for (int tt = 0; tt < TPS; ++tt) {
+                    const uint32_t acc = (uint32_t)(j * nacc * KS) + acc_idx[tt];
+                    uint32_t accum = 1u;
+                    if (s == 0) {   // first k-step of this slab: overwrite only if nobody has written this accumulator yet
+                      accum = (started_now >> acc) & 1u;
+#pragma unroll
+                      for (int t2 = 0; t2 < tt; ++t2) accum |= (acc_idx[t2] == acc_idx[tt]) ? 1u : 0u;
+                    }
+                    umma_bf16(tmem_acc + acc * (uint32_t)p.Ncta, a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
+                              b_base + tt * tap_stride16 + (uint32_t)((s * 32) >> 4), idesc, accum);
                   }
-                  umma_bf16(tmem_base + acc * (uint32_t)p.Ncta, a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
-                            b_base + tt * tap_stride16 + (uint32_t)((s * 32) >> 4), idesc, accum);
                 }
               }
             }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+              for (int tt = 0; tt < TPS; ++tt) started |= 1u << ((uint32_t)(j * nacc * KS) + acc_idx[tt]);
+            if (!p.mcast && elect_one()) tcgen05_commit(smem_u32(&w_empty[ws]));  // frees the slab when these MMAs retire
           }
           __syncwarp();
-#pragma unroll
-          for (int j = 0; j < J; ++j)
-#pragma unroll
-            for (int tt = 0; tt < TPS; ++tt) started |= 1u << ((uint32_t)(j * nacc * KS) + acc_idx[tt]);
-          if (elect_one()) tcgen05_commit(smem_u32(&w_empty[ws]));  // frees the weight slab when these MMAs retire
+          if (!p.mcast && ++ws == p.WST) { ws = 0; wph ^= 1; }
         }
+        if (elect_one()) tcgen05_commit(smem_u32(&halo_empty[hs]));
         __syncwarp();
-        if (++ws == p.WST) { ws = 0; wph ^= 1; }
+        if (++hs == p.HST) { hs = 0; hph ^= 1; }
       }
-      if (elect_one()) tcgen05_commit(smem_u32(&halo_empty[hs]));
+      if (elect_one()) tcgen05_commit(smem_u32(&acc_full[as]));
+      if (lane == 0 && it == 0) STAMP(5);
       __syncwarp();
-      if (++hs == p.HST) { hs = 0; hph ^= 1; }
     }
-    if (elect_one()) tcgen05_commit(smem_u32(acc_full));
-    if (lane == 0) STAMP(5);
-    __syncwarp();
-  } else if (warp >= 2 && active) {
-    // ===================== epilogue (warps 2..5) =====================
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
     for (int c = (int)threadIdx.x - 64; c < p.Ncta; c += 32 * NUM_EPI_WARPS) s_bias[c] = p.bias ? p.bias[n0 + c] : 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");   // the epilogue warps only
     pdl_wait();                                        // res / y belong to the dependency chain
@@ -390,95 +415,112 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     const int m = 32 * q + lane;       // accumulator row = pixel within the 16x8 sub-tile
     const int ry = m >> 3, rx = m & 7;
     const float act_slope = p.act == TECO_ACT_RELU ? 0.f : (p.act == TECO_ACT_LRELU02 ? 0.2f : 1.f);
-    mbar_wait_warp(smem_u32(acc_full), 0);
-    tcgen05_fence_after();
-    if (threadIdx.x == 64) STAMP(6);
-    const int oy_in = y0 + ry;
     // EW output channels per step: 32 (two steps for 64 channels) or 16 (the 16-channel fp32 output stage)
     auto run = [&](auto ew_tag) {
       constexpr int EW = decltype(ew_tag)::value;
-      for (int j = 0; j < J; ++j) {
-        const int ox_in = x0 + 8 * j + rx;
-        const bool in_img = (oy_in < p.H) && (ox_in < p.W);
-        for (int ph = 0; ph < nacc; ++ph) {
-          int oy, ox, OH, OW;
-          if (MODE == 1) {
-            oy = 2 * oy_in + (ph >> 1); ox = 2 * ox_in + (ph & 1); OH = 2 * p.H; OW = 2 * p.W;
-          } else {
-            oy = oy_in; ox = ox_in; OH = p.H; OW = p.W;
-          }
-          const size_t pix = ((size_t)n * OH + oy) * OW + ox;
-          const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((j * nacc + ph) * KS * p.Ncta);
-          for (int c0 = chalf * EW; c0 < p.Ncta; c0 += 2 * EW) {
-            uint32_t r[EW];
-            __syncwarp();
-            if (EW == 32) tmem_ld32(tcol + (uint32_t)c0, r); else tmem_ld16(tcol + (uint32_t)c0, r);
-            if (KS == 3) {   // K-split chains: issue all three TMEM loads, wait once, add
-              uint32_t r2[EW], r3[EW];
-              if (EW == 32) { tmem_ld32(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld32(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
-              else { tmem_ld16(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld16(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < EW; ++i)
-                r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]) + __uint_as_float(r3[i]));
+      for (int it = 0; it < my_tiles; ++it) {
+        int n, y0, x0;
+        tile_coords(it, n, y0, x0);
+        const int as = (p.AS == 2) ? (it & 1) : 0;
+        const uint32_t ause = (uint32_t)((p.AS == 2) ? (it >> 1) : it);
+        mbar_wait_warp(smem_u32(&acc_full[as]), ause & 1u);
+        tcgen05_fence_after();
+        if (threadIdx.x == 64 && it == 0) STAMP(6);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)as * acc_stage_cols;
+        const int oy_in = y0 + ry;
+        for (int j = 0; j < J; ++j) {
+          const int ox_in = x0 + 8 * j + rx;
+          const bool in_img = (oy_in < p.H) && (ox_in < p.W);
+          for (int ph = 0; ph < nacc; ++ph) {
+            int oy, ox, OH, OW;
+            if (MODE == 1) {
+              oy = 2 * oy_in + (ph >> 1); ox = 2 * ox_in + (ph & 1); OH = 2 * p.H; OW = 2 * p.W;
             } else {
-              tmem_wait_ld();
+              oy = oy_in; ox = ox_in; OH = p.H; OW = p.W;
             }
-            if (threadIdx.x == 64 && j == 0 && ph == 0 && c0 == 0) STAMP(11);
-            float v[EW];
+            const size_t pix = ((size_t)n * OH + oy) * OW + ox;
+            const uint32_t tcol = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)((j * nacc + ph) * KS * p.Ncta);
+            for (int c0 = chalf * EW; c0 < p.Ncta; c0 += 2 * EW) {
+              uint32_t r[EW];
+              __syncwarp();
+              if (EW == 32) tmem_ld32(tcol + (uint32_t)c0, r); else tmem_ld16(tcol + (uint32_t)c0, r);
+              if (KS == 3) {   // K-split chains: issue all three TMEM loads, wait once, add
+                uint32_t r2[EW], r3[EW];
+                if (EW == 32) { tmem_ld32(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld32(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
+                else { tmem_ld16(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld16(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
+                tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < EW; ++i) {
-              const float a = __uint_as_float(r[i]) + s_bias[c0 + i];
-              v[i] = fmaxf(a, a * act_slope);      // none: slope 1, relu: 0, lrelu: 0.2 -- no per-element branch
-            }
-            if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop
-#pragma unroll
-              for (int i = 0; i < EW; ++i) v[i] = teco_act(v[i], p.act);
-            }
-            if (!in_img) continue;
-            if (p.out_f32) {
-              for (int i = 0; i < EW; ++i) {
-                int c = n0 + c0 + i;
-                if (c < p.out_f32_c) {
-                  float a = v[i] + (p.res_f32 ? p.res_f32[pix * p.out_f32_c + c] : 0.f);
-                  p.out_f32[pix * p.out_f32_c + c] = a * p.post_scale + p.post_shift;
-                }
+                for (int i = 0; i < EW; ++i)
+                  r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]) + __uint_as_float(r3[i]));
+              } else {
+                tmem_wait_ld();
               }
-            }
-            if (p.y) {
-              if (p.res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + n0 + c0);
+              if (threadIdx.x == 64 && it == 0 && j == 0 && ph == 0 && c0 == 0) STAMP(11);
+              // last TMEM read of this tile by this warp -> hand the accumulator stage back to the MMA issuer
+              if (j == J - 1 && ph == nacc - 1 && c0 + 2 * EW >= p.Ncta) {
+                tcgen05_fence_before();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+              }
+              float v[EW];
 #pragma unroll
-                for (int k = 0; k < EW / 8; ++k) {
-                  const uint4 rr = rp[k];
-                  const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
-                    v[8 * k + 2 * i] += f.x;
-                    v[8 * k + 2 * i + 1] += f.y;
+              for (int i = 0; i < EW; ++i) {
+                const float a = __uint_as_float(r[i]) + s_bias[c0 + i];
+                v[i] = fmaxf(a, a * act_slope);      // none: slope 1, relu: 0, lrelu: 0.2 -- no per-element branch
+              }
+              if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop; rare (FNet head): keep it rolled
+#pragma unroll 1
+                for (int i = 0; i < EW; ++i) v[i] = teco_act(v[i], p.act);
+              }
+              if (!in_img) continue;
+              if (p.out_f32) {
+#pragma unroll 1
+                for (int i = 0; i < EW; ++i) {
+                  int c = n0 + c0 + i;
+                  if (c < p.out_f32_c) {
+                    float a = v[i] + (p.res_f32 ? p.res_f32[pix * p.out_f32_c + c] : 0.f);
+                    p.out_f32[pix * p.out_f32_c + c] = a * p.post_scale + p.post_shift;
                   }
                 }
               }
-              uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.Cout + n0 + c0);
+              if (p.y) {
+                if (p.res) {
+                  const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + n0 + c0);
 #pragma unroll
-              for (int k = 0; k < EW / 8; ++k) {
-                uint32_t o[4];
+                  for (int k = 0; k < EW / 8; ++k) {
+                    const uint4 rr = rp[k];
+                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
-                  o[i] = *reinterpret_cast<uint32_t*>(&h);
+                    for (int i = 0; i < 4; ++i) {
+                      float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+                      v[8 * k + 2 * i] += f.x;
+                      v[8 * k + 2 * i + 1] += f.y;
+                    }
+                  }
                 }
-                yp[k] = make_uint4(o[0], o[1], o[2], o[3]);
+                uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.Cout + n0 + c0);
+#pragma unroll
+                for (int k = 0; k < EW / 8; ++k) {
+                  uint32_t o[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                    o[i] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  yp[k] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
               }
+              if (threadIdx.x == 64 && it == 0 && j == 0 && ph == 0) STAMP(12 + ((c0 / EW) & 3));
             }
-            if (threadIdx.x == 64 && j == 0 && ph == 0) STAMP(12 + ((c0 / EW) & 3));
           }
+        }
+        // warps with no channel step of their own (16-channel output stage: chalf == 1) still release the stage
+        if (chalf * EW >= p.Ncta) {
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
         }
       }
     };
-    if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});
-    else run(std::integral_constant<int, 16>{});
+    if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});   // (a single EW = 16 instantiation halves the SASS but
+    else run(std::integral_constant<int, 16>{});                   //  measured 7.4 us vs 6.9 us on the 64->64 layer)
   }
 
   if (threadIdx.x == 64) STAMP(7);
@@ -530,12 +572,14 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
-long long* g_dbg_timing = nullptr;
-
 }  // namespace
 
+long long* teco_g_dbg_timing = nullptr;   // shared with conv_tc_sw.cu
+int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* wpk, const float* bias, const void* res,
+                             void* y, const float* res_f32, float* out_f32, void* stream);   // conv_tc_sw.cu
+
 extern "C" int teco_debug_timing(void* buf) {
-  g_dbg_timing = (long long*)buf;
+  teco_g_dbg_timing = (long long*)buf;
   return TECO_OK;
 }
 
@@ -576,69 +620,82 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.mode = d->mode; p.act = d->act; p.out_f32_c = d->out_f32_c;
   p.post_scale = d->post_scale; p.post_shift = d->post_shift;
   p.wpk = (const uint8_t*)wpk; p.bias = bias; p.res = (const __nv_bfloat16*)res; p.y = (__nv_bfloat16*)y;
-  p.res_f32 = res_f32; p.out_f32 = out_f32; p.dbg = g_dbg_timing;
+  p.res_f32 = res_f32; p.out_f32 = out_f32; p.dbg = teco_g_dbg_timing;
   p.nblk = d->Cin / CB;
-  p.HST = p.nblk > 1 ? 2 : 1;
-  // few spatial tiles but many output channels (FNet's 16x16 / 32x32 layers): split Cout over CTAs, 64 channels each
-  {
-    long long t1 = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8);
-    p.nsplit = (d->Cout >= 128 && d->Cout % 64 == 0 && t1 * (d->Cout / 64) <= 2LL * teco_sm_count()) ? d->Cout / 64 : 1;
-    p.Ncta = d->Cout / p.nsplit;
-  }
+  const int sms = teco_sm_count();
   const int nacc = d->mode == 1 ? 4 : 1;
   const size_t budget = 208 * 1024;
-  const int sms = teco_sm_count();
-  // sub-tiles per CTA: prefer the wider tile when it still yields >= 2 waves of CTAs and fits TMEM / smem
+  // few spatial tiles but many output channels (FNet's 16x16 / 32x32 layers): split Cout over CTAs, 64 channels each
+  const long long tiles1 = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8);
+  p.nsplit = (d->Cout >= 128 && d->Cout % 64 == 0 && tiles1 * (d->Cout / 64) <= 2LL * sms) ? d->Cout / 64 : 1;
+  p.Ncta = d->Cout / p.nsplit;
+  TECO_CHECK_ARG(nacc * p.Ncta <= 512, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
+  const size_t tap_bytes = (size_t)p.Ncta * 128;
+  const size_t copy1 = (size_t)HALO_ROWS * 8 * 128;            // one kx-copy of a J = 1 halo stage (18 KB)
+  const bool single_wave = tiles1 * p.nsplit <= (long long)sms;
+  // Dispatch (same-box A/B, profiles/conv_tc_r01_notes.md): the one-tile-per-CTA kernel is faster for single-wave
+  // launches and for the epilogue-heavy transposed conv (two CTAs per SM); this persistent kernel wins multi-wave convs.
+  if (single_wave || d->mode == 1) return teco_conv3x3_tc_one_tile(d, x, wpk, bias, res, y, res_f32, out_f32, stream);
+
+  // ---- configuration: (J, HST, weight staging, K-split, accumulator stages, grid)
   int J = 1;
-  for (int j = 2; j >= 1; --j) {
-    if (j * nacc * p.Ncta > 512) continue;
-    size_t a_bytes = (size_t)p.HST * 3 * HALO_ROWS * 8 * j * 128;
-    if (a_bytes + 2 * (size_t)p.Ncta * 128 > budget) continue;
-    long long tiles = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8 * j);
-    if (tiles >= 2LL * sms || j == 1) { J = j; break; }
+  p.mcast = 0; p.CS = 1; p.AS = 1;
+  if (single_wave) {
+    // One tile per CTA, one CTA per SM (e.g. the 128x128 trunk: 128 tiles).  Whole layer resident when it fits: fetched
+    // before the dependency wait and multicast over a 4-CTA cluster (measured 6.2 us vs 6.9 us for a ring, 64->64).
+    p.HST = p.nblk > 1 ? 2 : 1;
+    const size_t a_total1 = (size_t)p.HST * 3 * copy1;
+    if (p.nsplit == 1 && a_total1 + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
+      p.mcast = 1; p.TPS = 3; p.WST = 3 * p.nblk;
+      p.CS = tiles1 >= 8 ? 4 : 1;
+    } else if (p.nsplit == 1 && a_total1 + 2 * 3 * tap_bytes <= budget) {
+      p.TPS = 3; p.WST = (int)((budget - a_total1) / (3 * tap_bytes));
+      if (p.WST > 3 * p.nblk) p.WST = 3 * p.nblk;
+      if (p.WST > MAX_WST) p.WST = MAX_WST;
+    } else {
+      p.TPS = 1;
+      int wst = (int)((budget - a_total1) / tap_bytes);
+      if (wst > 9 * p.nblk) wst = 9 * p.nblk;
+      if (wst > MAX_WST) wst = MAX_WST;
+      TECO_CHECK_ARG(wst >= 2, "teco_conv3x3_tc: shared memory budget too small (Cin=%d Cout=%d)", d->Cin, d->Cout);
+      p.WST = wst;
+    }
+  } else {
+    // Multi-wave problems: persistent CTAs (one per SM) walking tiles, double-buffered halo stages and -- when TMEM
+    // allows -- two accumulator stages, so TMA, MMA and epilogue overlap across tiles; the layer's weights stay resident
+    // in shared memory for the whole launch when they fit next to two halo stages.
+    p.HST = 2;
+    const size_t a_total1 = 2 * 3 * copy1;                     // J = 1: 108 KB
+    if (a_total1 + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
+      p.mcast = 1; p.TPS = 3; p.WST = 3 * p.nblk;             // resident, loaded once per CTA (no cluster: CS = 1)
+    } else if (a_total1 + 2 * 3 * tap_bytes <= budget) {
+      p.TPS = 3; p.WST = (int)((budget - a_total1) / (3 * tap_bytes));
+      if (p.WST > MAX_WST) p.WST = MAX_WST;
+    } else {
+      p.TPS = 1;
+      int wst = (int)((budget - a_total1) / tap_bytes);
+      if (wst > MAX_WST) wst = MAX_WST;
+      TECO_CHECK_ARG(wst >= 2, "teco_conv3x3_tc: shared memory budget too small (Cin=%d Cout=%d)", d->Cin, d->Cout);
+      p.WST = wst;
+    }
   }
-  TECO_CHECK_ARG(J * nacc * p.Ncta <= 512, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
   p.J = J;
   p.tiles_x = teco_ceil_div(d->W, 8 * J);
   p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
+  p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
   p.copy_bytes = (uint32_t)(HALO_ROWS * 8 * J * 128);
   p.halo_stage_bytes = 3 * p.copy_bytes;
   const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
-  const size_t tap_bytes = (size_t)p.Ncta * 128;
-  // whole layer resident?  then 3 taps per slab (3 barriers per block), fetched once, multicast over a 4-CTA cluster
-  p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
-  // Weight staging.  Preferred: a 2-deep ring of 3-tap slabs -- with the halo copies that is ~105 KB, so TWO CTAs fit per SM
-  // and programmatic dependent launch really overlaps the next layer's prologue + weight prefetch with this layer's
-  // MMA/epilogue.  (A whole resident layer, 128 KB, multicast over a cluster, serialised the layers: round-1 notes.)
-  const size_t half_sm = 112 * 1024;
-  p.mcast = 0;
-  const bool single_wave = (long long)p.num_tiles * p.nsplit <= (long long)sms;
-  if (single_wave && p.nsplit == 1 && a_total + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
-    // one CTA per SM anyway (e.g. the 128x128 trunk: 128 tiles): whole layer resident, fetched before the dependency
-    // wait and multicast over a 4-CTA cluster -- measured 6.2 us vs 6.9 us for the ring on the 64->64 layer
-    p.mcast = 1; p.TPS = 3; p.WST = 3 * p.nblk;
-  } else if (p.nsplit == 1 && 1024 + a_total + 2 * 3 * tap_bytes + 1024 <= half_sm) {
-    // multi-wave grids: 2-deep ring of 3-tap slabs (~105 KB) so TWO CTAs share an SM (256x256: 14.7 us vs 24.0 us)
-    p.TPS = 3; p.WST = 2;
-  } else if (p.nsplit == 1 && a_total + 2 * 3 * tap_bytes <= budget) {
-    p.TPS = 3; p.WST = (int)((budget - a_total) / (3 * tap_bytes));
-    if (p.WST > 3 * p.nblk) p.WST = 3 * p.nblk;
-    if (p.WST > MAX_WST) p.WST = MAX_WST;
-  } else {
-    p.TPS = 1;
-    int wst = (int)((budget - a_total) / tap_bytes);
-    if (wst > 9 * p.nblk) wst = 9 * p.nblk;
-    if (wst > MAX_WST) wst = MAX_WST;
-    TECO_CHECK_ARG(wst >= 2, "teco_conv3x3_tc: shared memory budget too small (Cin=%d Cout=%d)", d->Cin, d->Cout);
-    p.WST = wst;
-  }
   p.w_slab_bytes = (uint32_t)(p.TPS * tap_bytes);
   p.KS = (p.TPS == 3 && d->mode == 0 && J * 3 * p.Ncta <= 512) ? 3 : 1;
-  p.CS = (p.mcast && p.num_tiles >= 8) ? 4 : 1;
-  uint32_t cols = (uint32_t)(J * nacc * p.KS * p.Ncta), tc = 32;
+  const uint32_t stage_cols = (uint32_t)(J * nacc * p.KS * p.Ncta);
+  if (!single_wave && 2 * stage_cols <= 512) p.AS = 2;
+  uint32_t cols = stage_cols * (uint32_t)p.AS, tc = 32;
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
-  const size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float);
+  if (single_wave) p.G = (p.num_tiles + p.CS - 1) / p.CS * p.CS;   // padded to the cluster size
+  else p.G = p.num_tiles < sms ? p.num_tiles : sms;
+  const size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 4 + 1) * 8 + 256 * sizeof(float);
 
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -669,8 +726,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     return TECO_E_UNSUPPORTED;
   }
   TECO_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
-  p.tiles_pad = (p.num_tiles + p.CS - 1) / p.CS * p.CS;
-  const unsigned ctas = (unsigned)(p.tiles_pad * p.nsplit);
+  const unsigned ctas = (unsigned)(p.G * p.nsplit);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(NUM_THREADS);
