@@ -237,21 +237,20 @@ conv2d_wgrad_f32_kernel(const teco_conv_desc d, const float* __restrict__ x, con
   }
 }
 
-// db[c] += sum over pixels of dy[pixel, c] (dy addressed through the output mapping).
+// db[c] += sum over pixels of dy[pixel, c] (dy addressed through the output mapping).  Threads are laid out
+// channel-fastest (coalesced), 256 / C pixel lanes per block, shared-memory reduce, one atomic per channel per block.
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const teco_conv_desc d, const float* __restrict__ dy, float* __restrict__ db, long long pix_per_block) {
+  __shared__ float part[256];
   const long long M = (long long)d.N * d.OH * d.OW;
   const long long p_begin = (long long)blockIdx.x * pix_per_block;
   const long long p_end = min(M, p_begin + pix_per_block);
-  // thread handles channel c = threadIdx.x % Cpad over a strided set of pixels
-  int cpt = d.Cout;  // channels
-  int lanes_per_pix = cpt;
-  int pix_par = max(1, 256 / lanes_per_pix);
-  int c = threadIdx.x % lanes_per_pix;
-  int ps = threadIdx.x / lanes_per_pix;
+  const int C = d.Cout;
+  const int ppar = 256 / C;                 // C <= 256
+  const int c = threadIdx.x % C, ps = threadIdx.x / C;
   float s = 0.f;
-  if (ps < pix_par) {
-    for (long long pm = p_begin + ps; pm < p_end; pm += pix_par) {
+  if (ps < ppar) {
+    for (long long pm = p_begin + ps; pm < p_end; pm += ppar) {
       long long t = pm;
       int ox = (int)(t % d.OW);
       t /= d.OW;
@@ -260,6 +259,11 @@ bias_grad_kernel(const teco_conv_desc d, const float* __restrict__ dy, float* __
       s += dy[(((long long)n * d.out_H + (oy * d.out_sy + d.out_oy)) * d.out_W + (ox * d.out_sx + d.out_ox)) *
                   d.out_cpitch + c];
     }
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (ps == 0) {
+    for (int k = 1; k < ppar; ++k) s += part[k * C + c];
     atomicAdd(&db[c], s);
   }
 }
@@ -320,8 +324,8 @@ extern "C" int teco_conv2d_wgrad_f32(const teco_conv_desc* d, const float* x, co
   TECO_CUDA_LAUNCH_CHECK("teco_conv2d_wgrad_f32");
   if (db) {
     TECO_CHECK_ARG(d->Cout <= 256, "teco_conv2d_wgrad_f32: bias gradient supports Cout <= 256 (got %d)", d->Cout);
-    long long blocks = (M + 4095) / 4096;
-    if (blocks > 2 * teco_sm_count()) blocks = 2 * teco_sm_count();
+    long long blocks = (M + 255) / 256;
+    if (blocks > 4 * teco_sm_count()) blocks = 4 * teco_sm_count();
     long long ppb = (M + blocks - 1) / blocks;
     blocks = (M + ppb - 1) / ppb;
     bias_grad_kernel<<<(unsigned)blocks, 256, 0, s>>>(*d, dy, db, ppb);

@@ -73,7 +73,9 @@ def conv_transpose2x_raw(x, w_oi, bias, y, *, pad, act=ACT_NONE):
             if not kys or not kxs:
                 y[:, a::2, b::2].zero_()
                 continue
-            wp = w_oi[kys][:, kxs].permute(0, 1, 3, 2).contiguous()  # [ty,tx,ci,co]
+            # (stack of slices, not list indexing: index tensors would need a host->device copy, which a CUDA graph cannot capture)
+            wp = torch.stack([torch.stack([w_oi[ky, kx] for kx in kxs], dim=0) for ky in kys], dim=0)
+            wp = wp.permute(0, 1, 3, 2).contiguous()  # [ty,tx,ci,co]
             conv2d_raw(x, wp, bias, y, stride=1, pad_t=pt, pad_l=pl, OH=H, OW=W, act=act, out_map=(2, a, 2, b))
     return y
 

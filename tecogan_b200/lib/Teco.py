@@ -22,10 +22,20 @@ VGG_LAYER_LABELS = ['vgg_19/conv2/conv2_2', 'vgg_19/conv3/conv3_4', 'vgg_19/conv
 _VGG_CFG = [(1, 2, 64), (2, 2, 128), (3, 4, 256), (4, 4, 512), (5, 4, 512)]
 
 
+_consts = {}
+
+
+def _const(key, make):
+    """Device constants are created once, outside any CUDA-graph capture (host->device copies cannot be captured)."""
+    if key not in _consts:
+        _consts[key] = make()
+    return _consts[key]
+
+
 def _vgg_raw(input_pm1):
     """vgg_19 conv trunk (reference lib/ops.py:287-334) on deprocess(x)*255 - mean; returns {scope: post-ReLU feature}."""
     x = K.affine_act(input_pm1, 127.5, 127.5)             # deprocess then *255  (lib/Teco.py:9-10)
-    mean = torch.tensor(VGG_MEAN, device=x.device, dtype=torch.float32)
+    mean = _const(("vgg_mean", x.device), lambda: torch.tensor(VGG_MEAN, device=x.device, dtype=torch.float32))
     x = x - mean                                           # per-channel constant shift (plumbing-sized op)
     out = {}
     with variable_scope('vgg_19'):
@@ -148,7 +158,7 @@ class _Graph:
             else:                   # :206-209 motion reused for the ping-pong sequence
                 v_pre = gen_flow[:, 0:t_size:3]
                 idx = list(range(T - 1))[-2:-1 - t_size:-3]
-                v_nxt = gen_flow[:, idx]
+                v_nxt = torch.stack([gen_flow[:, i] for i in idx], dim=1)
             T_vel = torch.stack((v_pre, torch.zeros_like(v_pre), v_nxt), dim=2).reshape(B * t_size, H, H, 2).detach()
             if FLAGS.crop_dt < 1.0:  # :216-220
                 crop_size_dt = int(crop * 4 * FLAGS.crop_dt)
@@ -275,7 +285,10 @@ class _TrainState:
 
     def __init__(self, r_inputs, r_targets, FLAGS, GAN_Flag):
         self.FLAGS, self.GAN = FLAGS, GAN_Flag
-        self.r_inputs, self.r_targets = r_inputs, r_targets
+        self.static_in = r_inputs.detach().clone().contiguous()      # static buffers: the captured step reads these
+        self.static_tg = r_targets.detach().clone().contiguous()
+        self.use_graph = bool(getattr(FLAGS, 'train_cuda_graph', True))
+        self.graph = None
         self.store = default_store()
         self.global_step = 0
         self.tb_ema = 0.0
@@ -309,22 +322,21 @@ class _TrainState:
             p = math.floor(p)
         return F.learning_rate * (F.decay_rate ** p)
 
-    def __call__(self, r_inputs=None, r_targets=None):
+    def _compute(self):
+        """Forward over the unrolled recurrence, every loss, backward, and the flat bucket
+        [G grads | FNet grads | D grads | t_balance | loss scalars] -- no host synchronisation, so the whole thing can be
+        captured in one CUDA graph (about 2000 kernel launches for case 4, 6000 for case 3)."""
+        from .. import config
         F = self.FLAGS
-        if r_inputs is not None:
-            self.r_inputs, self.r_targets = r_inputs, r_targets
         st = self.store
-        leaves = {}
-        for k in self.names:                       # fresh leaf views of the flat parameter buffers
-            leaves[k] = st[k].detach().requires_grad_(True)
+        leaves = {k: st[k].detach().requires_grad_(True) for k in self.names}   # fresh leaf views of the flat buffers
         saved = {k: st[k] for k in self.names}
         for k in self.names:
             st[k] = leaves[k]
-        from .. import config
         prev_precision = config.precision()
         try:
             config.set_precision("fp32")
-            g = _Graph(self.r_inputs, self.r_targets, F, self.GAN, self.global_step)
+            g = _Graph(self.static_in, self.static_tg, F, self.GAN, self.global_step)
             gf = self.opt_g.names + self.opt_f.names
             grads = torch.autograd.grad(g.fnet_loss, [leaves[k] for k in gf], retain_graph=self.GAN, allow_unused=True)
             d_grads = ()
@@ -334,7 +346,6 @@ class _TrainState:
             config.set_precision(prev_precision)
             for k in self.names:
                 st[k] = saved[k]
-        # ---- one flat bucket: grads + control scalars (+ loss scalars for logging)
         b = self.bucket
         o = 0
         for k, gr in zip(gf + (self.opt_d.names if self.GAN else []), list(grads) + list(d_grads)):
@@ -345,11 +356,36 @@ class _TrainState:
                 b[o:o + n].copy_(gr.reshape(-1))
             o += n
         scal = [g.t_balance if self.GAN else torch.zeros((), device=b.device)] + list(g.update_list)
-        scal = torch.stack([s.detach().float() if torch.is_tensor(s) else torch.tensor(float(s), device=b.device) for s in scal])
+        scal = torch.stack([s_.detach().float() if torch.is_tensor(s_) else torch.full((), float(s_), device=b.device) for s_ in scal])
         b[o:o + scal.numel()].copy_(scal)
+        self._scal_off, self._n_scal = o, scal.numel()
+        self._names_now = g.update_list_name
+        self._gen_outputs = g.gen_outputs.detach()
+
+    def __call__(self, r_inputs=None, r_targets=None):
+        F = self.FLAGS
+        if r_inputs is not None:
+            self.static_in.copy_(r_inputs)
+            self.static_tg.copy_(r_targets)
+        if self.use_graph and F.Dt_ratio_add == 0.0:
+            if self.graph is None:
+                # warm-up on a side stream (lazy initialisations, allocator), then capture the whole step once
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._compute()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._compute()
+            self.graph.replay()
+        else:
+            self._compute()
+        b, o = self.bucket, self._scal_off
         from ..parallel import allreduce_bucket, decide_with_d
         inv = allreduce_bucket(b)                   # the single NCCL all-reduce of the step (sum); inv = 1/world
-        scal_host = (b[o:o + scal.numel()] * inv).tolist()       # one small D2H: drives the tb < Dbalance branch + logging
+        scal_host = (b[o:o + self._n_scal] * inv).tolist()       # one small D2H: drives the tb < Dbalance branch + logging
         lr = self.learning_rate()
         ng, nf = self.opt_g.n, self.opt_f.n
         with_d = False
@@ -362,14 +398,14 @@ class _TrainState:
                 self.counter2 += 1
         self.opt_g.step(b[0:ng], lr, inv)
         self.opt_f.step(b[ng:ng + nf], lr, inv)
-        st.touch()
+        self.store.touch()
         vals = scal_host[1:]
         if self.loss_ema is None:
             self.loss_ema = [0.0] * len(vals)
-        self.loss_ema = [0.99 * a + 0.01 * v for a, v in zip(self.loss_ema, vals)]
+        self.loss_ema = [0.99 * a_ + 0.01 * v for a_, v in zip(self.loss_ema, vals)]
         self.global_step += 1
-        self.last = {"update_list": vals, "update_list_name": g.update_list_name, "with_d": with_d, "lr": lr,
-                     "gen_outputs": g.gen_outputs.detach(), "t_balance": scal_host[0], "tb_ema": self.tb_ema}
+        self.last = {"update_list": vals, "update_list_name": self._names_now, "with_d": with_d, "lr": lr,
+                     "gen_outputs": self._gen_outputs, "t_balance": scal_host[0], "tb_ema": self.tb_ema}
         return self.last
 
     def update_list_avg(self):

@@ -58,7 +58,7 @@ def test_transposed_conv_phase_decomposition(K, pad):
         kys, pt = _phase_taps(K, pad, a)
         for b in (0, 1):
             kxs, pl = _phase_taps(K, pad, b)
-            wp = w_oi[kys][:, kxs].permute(0, 1, 3, 2)                        # [ty,tx,ci,co]
+            wp = torch.stack([torch.stack([w_oi[ky, kx] for kx in kxs], dim=0) for ky in kys], dim=0).permute(0, 1, 3, 2)
             xp = F.pad(x.permute(0, 3, 1, 2), (pl, len(kxs) - 1 - pl, pt, len(kys) - 1 - pt))
             y[:, a::2, b::2] = F.conv2d(xp, wp.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
     if K == 3:

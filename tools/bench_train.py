@@ -27,9 +27,17 @@ st.load(xavier_params(1, F.num_resblock, gan, F.vgg_scaling > 0))
 dev = torch.device("cuda")
 lr, tg = frvsr_gpu_data_loader(M.synthetic_hr_batch(F, 0, 0, dev), F)
 Net = TecoGAN(lr, tg, F) if gan else FRVSR(lr, tg, F)
+if os.environ.get("TECO_TRAIN_NOGRAPH"):
+    Net.train.use_graph = False
 for i in range(2):
     r = Net.train()
 torch.cuda.synchronize()
+if os.environ.get("TECO_TRAIN_PROFILE"):      # one eager step inside a profiler range (ncu --profile-from-start off)
+    torch.cuda.profiler.start()
+    Net.train()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 t0 = time.perf_counter()
 for i in range(steps):
     r = Net.train()
