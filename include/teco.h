@@ -84,6 +84,8 @@ typedef struct teco_tc_desc {
   float post_scale, post_shift;
 } teco_tc_desc;
 
+/* transpose_layout bit 0: w is [3,3,cout,cin] (conv_transpose layout); bit 1: taps flipped (ky,kx) -> (2-ky,2-kx).
+ * Value 3 with (cin, cout) = (Cout, Cin) of a forward conv packs its input-gradient convolution. */
 int teco_pack_conv3x3_bf16(const float* w, int32_t cin, int32_t cout, int32_t cin_pad, int32_t cout_pad,
                            int32_t transpose_layout, const int32_t* cin_perm, void* wpk, void* stream);
 int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad);
@@ -150,6 +152,12 @@ int teco_f32_to_bf16_pad(const float* src, void* dst, int64_t npix, int32_t C, i
                          int32_t dst_cpitch, int32_t c_off, float scale, float shift, void* stream);
 int teco_bf16_to_f32(const void* src, float* dst, int64_t npix, int32_t C, int32_t src_cpitch, int32_t dst_cpitch,
                      void* stream);
+/* dst[p, c] = float(src[p, c]) + (add ? add[p, c] : 0) for c < C; dst/add pitch = dst_cpitch */
+int teco_bf16_to_f32_add(const void* src, const float* add, float* dst, int64_t npix, int32_t C, int32_t src_cpitch,
+                         int32_t dst_cpitch, void* stream);
+/* dst[p, c] = bf16(src[p, c]) for c < C, 0 for C <= c < dst_cpitch (whole padded row written) */
+int teco_f32_to_bf16_rowpad(const float* src, void* dst, int64_t npix, int32_t C, int32_t src_cpitch, int32_t dst_cpitch,
+                            void* stream);
 /* save_img quantisation lib/ops.py:521-523: clip(x*255,0,255) -> uint8 (truncation), RGB order kept. */
 int teco_to_u8(const float* x, uint8_t* y, int64_t n, void* stream);
 

@@ -124,6 +124,8 @@ def train(FLAGS):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from tecogan_b200 import config
+    config.set_train_precision(FLAGS.precision)   # bf16: tcgen05 forward + input-gradient convs, fp32 master weights
     store = V.set_default_store(V.VariableStore(seed=FLAGS.rand_seed))   # same seed on every rank -> identical init
     gan = FLAGS.ratio > 0
     if FLAGS.checkpoint is not None:

@@ -60,6 +60,8 @@ SIGNATURES = {
     "teco_act_bwd_f32": [_P, _P, _P, _I64, _I32, _P],
     "teco_f32_to_bf16_pad": [_P, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P],
     "teco_bf16_to_f32": [_P, _P, _I64, _I32, _I32, _I32, _P],
+    "teco_bf16_to_f32_add": [_P, _P, _P, _I64, _I32, _I32, _I32, _P],
+    "teco_f32_to_bf16_rowpad": [_P, _P, _I64, _I32, _I32, _I32, _P],
     "teco_to_u8": [_P, _P, _I64, _P],
     "teco_bn_train_f32": [_P, _P, _P, _P, _I64, _I32, _F, _I32, _P],
     "teco_bn_train_bwd_f32": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _P],

@@ -1,5 +1,5 @@
 """Run-time configuration of the compute path (not part of the reference interface)."""
-_cfg = {"precision": "bf16"}
+_cfg = {"precision": "bf16", "train_precision": "fp32"}
 
 
 def set_precision(p):
@@ -15,3 +15,15 @@ def precision():
 
 def use_tensor_cores():
     return _cfg["precision"] == "bf16"
+
+
+def set_train_precision(p):
+    """'fp32' (default, exact parity with the oracle) or 'bf16': 3x3 stride-1 convolutions of the training graph run
+    forward + input-gradient on the tcgen05 kernel (bf16 operands, fp32 accumulation, fp32 master weights)."""
+    if p not in ("bf16", "fp32"):
+        raise ValueError("train precision must be 'bf16' or 'fp32'")
+    _cfg["train_precision"] = p
+
+
+def train_precision():
+    return _cfg["train_precision"]

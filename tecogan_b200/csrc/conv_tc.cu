@@ -550,8 +550,9 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, int cin, int co
     int ci = blk * 64 + j * 8 + e;
     int src_ci = cin_perm ? cin_perm[ci] : (ci < cin ? ci : -1);
     float v = 0.f;
+    const int stap = (transpose_layout & 2) ? 8 - tap : tap;   // bit 1: spatially flipped taps (input-gradient convolution)
     if (src_ci >= 0 && src_ci < cin && co < cout)
-      v = transpose_layout ? w[((long long)tap * cout + co) * cin + src_ci] : w[((long long)tap * cin + src_ci) * cout + co];
+      v = (transpose_layout & 1) ? w[((long long)stap * cout + co) * cin + src_ci] : w[((long long)stap * cin + src_ci) * cout + co];
     out[i] = __float2bfloat16_rn(v);
   }
 }

@@ -405,3 +405,46 @@ extern "C" int teco_l2norm_channels_f32(const float* f, float* y, int64_t npix, 
   TECO_CUDA_LAUNCH_CHECK("teco_l2norm_channels_f32");
   return TECO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// conversions used by the bf16 tensor-core training path
+namespace {
+__global__ void bf16_to_f32_add_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ add,
+                                       float* __restrict__ dst, long long npix, int C, int src_cpitch, int dst_cpitch) {
+  long long total = npix * C;
+  GRID_STRIDE(i, total) {
+    long long p = i / C;
+    int c = (int)(i - p * C);
+    float v = __bfloat162float(src[p * src_cpitch + c]);
+    if (add) v += add[p * dst_cpitch + c];
+    dst[p * dst_cpitch + c] = v;
+  }
+}
+__global__ void f32_to_bf16_rowpad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long npix,
+                                          int C, int src_cpitch, int dst_cpitch) {
+  long long total = npix * dst_cpitch;
+  GRID_STRIDE(i, total) {
+    long long p = i / dst_cpitch;
+    int c = (int)(i - p * dst_cpitch);
+    dst[i] = __float2bfloat16_rn(c < C ? src[p * src_cpitch + c] : 0.f);
+  }
+}
+}  // namespace
+
+extern "C" int teco_bf16_to_f32_add(const void* src, const float* add, float* dst, int64_t npix, int32_t C,
+                                    int32_t src_cpitch, int32_t dst_cpitch, void* stream) {
+  TECO_CHECK_ARG(src && dst && npix > 0 && C > 0 && src_cpitch >= C && dst_cpitch >= C, "teco_bf16_to_f32_add: bad argument");
+  bf16_to_f32_add_kernel<<<grid_for(npix * C), TPB, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, add, dst, npix, C,
+                                                                            src_cpitch, dst_cpitch);
+  TECO_CUDA_LAUNCH_CHECK("teco_bf16_to_f32_add");
+  return TECO_OK;
+}
+
+extern "C" int teco_f32_to_bf16_rowpad(const float* src, void* dst, int64_t npix, int32_t C, int32_t src_cpitch,
+                                       int32_t dst_cpitch, void* stream) {
+  TECO_CHECK_ARG(src && dst && npix > 0 && C > 0 && src_cpitch >= C && dst_cpitch >= C, "teco_f32_to_bf16_rowpad: bad argument");
+  f32_to_bf16_rowpad_kernel<<<grid_for(npix * dst_cpitch), TPB, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, npix, C,
+                                                                                        src_cpitch, dst_cpitch);
+  TECO_CUDA_LAUNCH_CHECK("teco_f32_to_bf16_rowpad");
+  return TECO_OK;
+}

@@ -477,7 +477,7 @@ def adam_step(p, m, v, g, lr_t, b1, b2, eps, gscale=1.0):
 def packed_weight(w, cin_pad, cout_pad, transpose_layout=False, cin_perm=None):
     """fp32 TF-layout weights -> UMMA-canonical bf16 slab [9][cin_pad/8][cout_pad][8] (device side)."""
     w = _cc(w)
-    if transpose_layout:
+    if int(transpose_layout) & 1:
         cout, cin = w.shape[2], w.shape[3]
     else:
         cin, cout = w.shape[2], w.shape[3]
@@ -546,3 +546,89 @@ def warp_s2d_fused(pre_gen, flow_lr, dst, ch_off, in_scale=1.0, in_shift=0.0, wa
     call("teco_warp_s2d_fused", ptr(pre_gen, f32), ptr(flow_lr, f32), ptr(dst), ptr(warped_out, f32), N, h, w,
          flow_lr.shape[1], flow_lr.shape[2], Cp, ch_off, int(dst.dtype == bf16), float(in_scale), float(in_shift), stream_ptr())
     return dst
+
+
+# ------------------------------------------------------------------------------------------ bf16 tensor-core TRAINING convs
+# bf16 compute, fp32 master weights / activations at the autograd boundary (north_star: "bf16 training").  Forward and the
+# input gradient run on the tcgen05 kernel (the input gradient of a 3x3 stride-1 SAME conv is the same conv with the taps
+# flipped and Cin/Cout swapped: teco_pack_conv3x3_bf16 flag 3); the weight gradient stays on the fp32 kernel.
+_tc_wcache = {}
+
+
+def tc_cache_clear():
+    """Packed bf16 weights are valid for one training step only (call at the start of every step / graph capture)."""
+    _tc_wcache.clear()
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def _tc_packed(w, b, flags, cin_pad, cout_pad):
+    key = (w.data_ptr(), flags)
+    hit = _tc_wcache.get(key)
+    if hit is None:
+        wpk = packed_weight(w.detach(), cin_pad, cout_pad, flags)
+        bp = None
+        if b is not None:
+            bp = torch.zeros(cout_pad, device=w.device, dtype=f32)
+            bp[: b.numel()].copy_(b.detach())
+        hit = _tc_wcache[key] = (wpk, bp)
+    return hit
+
+
+def _to_bf16_rows(x, cpad):
+    N, H, W, C = x.shape
+    xb = torch.empty((N, H, W, cpad), device=x.device, dtype=bf16)
+    call("teco_f32_to_bf16_rowpad", ptr(x, f32), ptr(xb, bf16), N * H * W, C, C, cpad, stream_ptr())
+    return xb
+
+
+def _from_bf16_rows(yb, C, add=None):
+    N, H, W, Cp = yb.shape
+    y = torch.empty((N, H, W, C), device=yb.device, dtype=f32)
+    call("teco_bf16_to_f32_add", ptr(yb, bf16), ptr(add, f32), ptr(y, f32), N * H * W, C, Cp, C, stream_ptr())
+    return y
+
+
+class _Conv3x3TC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act, res):
+        x, w = _cc(x), _cc(w)
+        if act != ACT_NONE and res is not None:
+            raise ValueError("conv2d: fused activation and residual are mutually exclusive")
+        Cin, Cout = w.shape[2], w.shape[3]
+        cip, cop = _pad64(Cin), _pad64(Cout)
+        wpk, bp = _tc_packed(w, b, 0, cip, cop)
+        yb = conv3x3_tc(_to_bf16_rows(x, cip), wpk, bp, cout=cop, act=act)
+        y = _from_bf16_rows(yb, Cout, None if res is None else _cc(res))
+        ctx.cfg = (act, b is not None, res is not None)
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        act, has_b, has_res = ctx.cfg
+        x, w, y = ctx.saved_tensors
+        dy = _cc(dy)
+        dz = dy
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("teco_act_bwd_f32", ptr(y, f32), ptr(dy, f32), ptr(dz, f32), dy.numel(), act, stream_ptr())
+        N, H, W, Cin = x.shape
+        Cout = w.shape[3]
+        cip, cop = _pad64(Cin), _pad64(Cout)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wpk_t, _ = _tc_packed(w, None, 3, cop, cip)          # flipped taps, Cin <-> Cout
+            dxb = conv3x3_tc(_to_bf16_rows(dz, cop), wpk_t, None, cout=cip, act=ACT_NONE)
+            dx = _from_bf16_rows(dxb, Cin)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = torch.empty(Cout, device=x.device, dtype=f32) if has_b and ctx.needs_input_grad[2] else None
+            conv2d_wgrad_raw(x, dz, dw, db, stride=1, pad_t=1, pad_l=1, OH=H, OW=W)
+        return dx, dw, db, None, (dy if has_res else None)
+
+
+def conv3x3_train_tc(x, w, b=None, act=ACT_NONE, res=None):
+    return _Conv3x3TC.apply(x, w, b, act, res)

@@ -327,6 +327,7 @@ class _TrainState:
         [G grads | FNet grads | D grads | t_balance | loss scalars] -- no host synchronisation, so the whole thing can be
         captured in one CUDA graph (about 2000 kernel launches for case 4, 6000 for case 3)."""
         from .. import config
+        K.tc_cache_clear()
         F = self.FLAGS
         st = self.store
         leaves = {k: st[k].detach().requires_grad_(True) for k in self.names}   # fresh leaf views of the flat buffers

@@ -3,6 +3,7 @@ Every function keeps the reference name and argument meaning; arithmetic runs in
 import numpy as np
 import torch
 
+from .. import config
 from .. import kernels as K
 from .._ffi import ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_TANH24, ACT_SIGMOID  # noqa: F401
 from ..variables import get_variable, variable_scope
@@ -51,6 +52,9 @@ def conv2(batch_input, kernel=3, output_channel=64, stride=1, use_bias=True, sco
         w = get_variable('weights', (kernel, kernel, cin, output_channel),
                          fans=(kernel * kernel * cin, kernel * kernel * output_channel))
         b = get_variable('biases', (output_channel,), init='zeros') if use_bias else None
+    if (kernel == 3 and stride == 1 and torch.is_grad_enabled() and config.train_precision() == "bf16"
+            and act in (ACT_NONE, ACT_RELU, ACT_LRELU02) and output_channel >= 16):
+        return K.conv3x3_train_tc(batch_input, w, b, act, res)      # tcgen05 forward + input gradient
     return K.conv2d(batch_input, w, b, stride, act, res)
 
 

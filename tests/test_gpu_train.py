@@ -147,3 +147,28 @@ def test_gauss_down_loader_matches_oracle():
     ref_lr = O.gauss_down_by4(hr.reshape(4, 40, 40, 3)).reshape(2, 2, 8, 8, 3)
     assert (lr.cpu() - ref_lr).abs().max().item() < 1e-5
     assert (tgt.cpu() - (hr[:, :, 4:36, 4:36] * 2 - 1)).abs().max().item() < 1e-6
+
+
+def test_bf16_tensor_core_training_step_close_to_fp32_oracle():
+    """--precision bf16 for training: 3x3 convs run forward + input-gradient on tcgen05 (bf16 operands, fp32 accumulate,
+    fp32 master weights).  Losses within 2e-2 relative of the fp32 oracle, gradient direction preserved (cosine > 0.99)."""
+    from tecogan_b200 import config
+    from tecogan_b200.lib.Teco import FRVSR
+    g, FL, P = _case("frvsr")
+    ri, rt = torch.from_numpy(g["r_inputs"]), torch.from_numpy(g["r_targets"])
+    tr = O.Trainer(P, FL, False)
+    ref = tr.step(ri, rt)
+    _fresh_store(P)
+    config.set_train_precision("bf16")
+    try:
+        net = FRVSR(ri.cuda(), rt.cuda(), FL)
+        out = net.train()
+    finally:
+        config.set_train_precision("fp32")
+    want = np.array([float(v) for v in ref["update_list"]])
+    np.testing.assert_allclose(np.array(out["update_list"]), want, rtol=2e-2, atol=1e-4)
+    st = net.train
+    got = st.bucket[:st.opt_g.n + st.opt_f.n].cpu()
+    refg = torch.cat([ref["grads"][k].reshape(-1) for k in st.opt_g.names + st.opt_f.names])
+    cos = float((got * refg).sum() / (got.norm() * refg.norm()))
+    assert cos > 0.99, cos

@@ -22,6 +22,8 @@ else:
     F = M.parse_flags(["--mode", "train", "--output_dir", "/tmp/x", "--num_resblock", "16", "--ratio", "0.01", "--pingpang",
                        "--pp_scaling", "0.5", "--vgg_scaling", "0.2", "--learning_rate", "0.00005", "--decay_rate", "1.0", "--stair"])
 gan = F.ratio > 0
+from tecogan_b200 import config  # noqa: E402
+config.set_train_precision(os.environ.get("TECO_TRAIN_PRECISION", "fp32"))
 st = V.set_default_store(V.VariableStore())
 st.load(xavier_params(1, F.num_resblock, gan, F.vgg_scaling > 0))
 dev = torch.device("cuda")
@@ -43,6 +45,6 @@ for i in range(steps):
     r = Net.train()
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / steps
-print("%s: %.1f ms/step  -> %.1f unique HR frames/s (B=%d x RNN_N=%d); losses %s" % (
-    which, dt * 1e3, F.batch_size * F.RNN_N / dt, F.batch_size, F.RNN_N,
+print("%s [%s]: %.1f ms/step  -> %.1f unique HR frames/s (B=%d x RNN_N=%d); losses %s" % (
+    which, config.train_precision(), dt * 1e3, F.batch_size * F.RNN_N / dt, F.batch_size, F.RNN_N,
     dict(zip(r["update_list_name"], [round(v, 5) for v in r["update_list"]]))))
