@@ -608,7 +608,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   TECO_CHECK_ARG(y || out_f32, "teco_conv3x3_tc: no output buffer");
   TECO_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0, "teco_conv3x3_tc: bad shape N=%d H=%d W=%d", d->N, d->H, d->W);
   TECO_CHECK_ARG(d->Cin >= 64 && d->Cin % 64 == 0 && d->Cin <= 512, "teco_conv3x3_tc: Cin must be a multiple of 64 in [64,512] (got %d)", d->Cin);
-  TECO_CHECK_ARG(d->Cout >= 16 && d->Cout % 16 == 0 && d->Cout <= 256, "teco_conv3x3_tc: Cout must be a multiple of 16 in [16,256] (got %d)", d->Cout);
+  TECO_CHECK_ARG(d->Cout >= 16 && d->Cout % 16 == 0 && d->Cout <= 512, "teco_conv3x3_tc: Cout must be a multiple of 16 in [16,512] (got %d)", d->Cout);
   TECO_CHECK_ARG(d->mode == 0 || d->mode == 1, "teco_conv3x3_tc: unknown mode %d", d->mode);
   TECO_CHECK_ARG(d->act >= 0 && d->act <= TECO_ACT_SIGMOID, "teco_conv3x3_tc: unknown activation %d", d->act);
   TECO_CHECK_ARG(!out_f32 || (d->out_f32_c > 0 && d->out_f32_c <= d->Cout), "teco_conv3x3_tc: bad out_f32_c");
@@ -629,6 +629,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   // few spatial tiles but many output channels (FNet's 16x16 / 32x32 layers): split Cout over CTAs, 64 channels each
   const long long tiles1 = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8);
   p.nsplit = (d->Cout >= 128 && d->Cout % 64 == 0 && tiles1 * (d->Cout / 64) <= 2LL * sms) ? d->Cout / 64 : 1;
+  if (d->Cout / p.nsplit > 256) p.nsplit = d->Cout / 256;   // VGG's 512-channel layers: N <= 256 per UMMA / TMEM stage
   p.Ncta = d->Cout / p.nsplit;
   TECO_CHECK_ARG(nacc * p.Ncta <= 512, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
   const size_t tap_bytes = (size_t)p.Ncta * 128;

@@ -520,7 +520,7 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   TECO_CHECK_ARG(y || out_f32, "teco_conv3x3_tc(one-tile): no output buffer");
   TECO_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0, "teco_conv3x3_tc(one-tile): bad shape N=%d H=%d W=%d", d->N, d->H, d->W);
   TECO_CHECK_ARG(d->Cin >= 64 && d->Cin % 64 == 0 && d->Cin <= 512, "teco_conv3x3_tc(one-tile): Cin must be a multiple of 64 in [64,512] (got %d)", d->Cin);
-  TECO_CHECK_ARG(d->Cout >= 16 && d->Cout % 16 == 0 && d->Cout <= 256, "teco_conv3x3_tc(one-tile): Cout must be a multiple of 16 in [16,256] (got %d)", d->Cout);
+  TECO_CHECK_ARG(d->Cout >= 16 && d->Cout % 16 == 0 && d->Cout <= 512, "teco_conv3x3_tc(one-tile): Cout must be a multiple of 16 in [16,512] (got %d)", d->Cout);
   TECO_CHECK_ARG(d->mode == 0 || d->mode == 1, "teco_conv3x3_tc(one-tile): unknown mode %d", d->mode);
   TECO_CHECK_ARG(d->act >= 0 && d->act <= TECO_ACT_SIGMOID, "teco_conv3x3_tc(one-tile): unknown activation %d", d->act);
   TECO_CHECK_ARG(!out_f32 || (d->out_f32_c > 0 && d->out_f32_c <= d->Cout), "teco_conv3x3_tc(one-tile): bad out_f32_c");
@@ -540,6 +540,7 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   {
     long long t1 = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8);
     p.nsplit = (d->Cout >= 128 && d->Cout % 64 == 0 && t1 * (d->Cout / 64) <= 2LL * teco_sm_count()) ? d->Cout / 64 : 1;
+    if (d->Cout / p.nsplit > 256) p.nsplit = d->Cout / 256;
     p.Ncta = d->Cout / p.nsplit;
   }
   const int nacc = d->mode == 1 ? 4 : 1;

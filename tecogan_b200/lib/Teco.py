@@ -48,7 +48,11 @@ def _vgg_raw(input_pm1):
                         from ..variables import get_variable
                         w = get_variable('weights', (3, 3, cin, cout), fans=(9 * cin, 9 * cout))
                         b = get_variable('biases', (cout,), init='zeros')
-                    x = K.conv2d(x, w, b, 1, ACT_RELU)      # slim.conv2d default activation relu, SAME (lib/Teco.py:12)
+                    from .. import config
+                    if config.train_precision() == "bf16":
+                        x = K.conv3x3_train_tc(x, w, b, ACT_RELU)     # frozen weights: forward (+ input gradient) on tcgen05
+                    else:
+                        x = K.conv2d(x, w, b, 1, ACT_RELU)      # slim.conv2d default activation relu, SAME (lib/Teco.py:12)
                     out['vgg_19/conv%d/%s' % (blk, name)] = x
             if blk < 5:
                 x = maxpool(x)

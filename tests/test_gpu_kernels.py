@@ -247,6 +247,7 @@ def _xpad(x):
 @pytest.mark.parametrize("n,h,w,cin,cout,act", [
     (1, 16, 8, 64, 64, 0), (1, 32, 32, 64, 64, 1), (2, 48, 40, 64, 64, 2), (1, 19, 21, 16, 32, 2), (1, 32, 32, 32, 64, 0),
     (1, 16, 16, 128, 256, 2), (1, 16, 24, 256, 128, 2), (1, 64, 64, 64, 16, 0), (1, 128, 128, 64, 64, 1), (3, 32, 32, 128, 128, 0),
+    (2, 16, 16, 512, 512, 1), (1, 32, 32, 256, 512, 1), (4, 64, 64, 256, 256, 1), (24, 32, 32, 512, 512, 1), (2, 256, 256, 64, 64, 1),
 ])
 def test_conv3x3_tc_matches_oracle_on_bf16_operands(n, h, w, cin, cout, act):
     from tecogan_b200 import kernels as K

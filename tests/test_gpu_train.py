@@ -172,3 +172,23 @@ def test_bf16_tensor_core_training_step_close_to_fp32_oracle():
     refg = torch.cat([ref["grads"][k].reshape(-1) for k in st.opt_g.names + st.opt_f.names])
     cos = float((got * refg).sum() / (got.norm() * refg.norm()))
     assert cos > 0.99, cos
+
+
+def test_bf16_tensor_core_tecogan_step_with_vgg_close_to_fp32_oracle():
+    """Same for the full TecoGAN graph: VGG19 (frozen, up to 512 channels) also runs on tcgen05 in bf16 mode."""
+    from tecogan_b200 import config
+    from tecogan_b200.lib.Teco import TecoGAN
+    g, FL, P = _case("teco_pp")
+    ri, rt = torch.from_numpy(g["r_inputs"]), torch.from_numpy(g["r_targets"])
+    tr = O.Trainer(P, FL, True)
+    ref = tr.step(ri, rt)
+    _fresh_store(P)
+    config.set_train_precision("bf16")
+    try:
+        net = TecoGAN(ri.cuda(), rt.cuda(), FL)
+        out = net.train()
+    finally:
+        config.set_train_precision("fp32")
+    want = np.array([float(v) for v in ref["update_list"]])
+    np.testing.assert_allclose(np.array(out["update_list"]), want, rtol=4e-2, atol=2e-3)
+    assert out["with_d"] == ref["with_d"]
