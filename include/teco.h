@@ -92,6 +92,15 @@ int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad);
 int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void* wpk, const float* bias,
                     const void* res, void* y, const float* res_f32, float* out_f32, void* stream);
 
+/* Fused generator trunk (reference lib/frvsr.py:59-70): input conv + N residual blocks = num_layers = 2N+1 layers of
+ * 3x3 64->64 in ONE launch; tiles hand over to their neighbours through per-tile counters instead of kernel boundaries.
+ * x_in / buf_a / buf_b: NHWC bf16 [N,H,W,64]; layer 0: x_in -> a (ReLU); odd l: a -> b (ReLU); even l >= 2: b -> a, + a.
+ * wpk_all: num_layers packed layers back to back (teco_pack_conv3x3_bf16, 64x64); bias_all: [num_layers][64] fp32;
+ * flags: num_tiles uint32 scratch.  Only shapes with tiles(16x8) <= SM count (teco_trunk64_supported) -- the result is in buf_a. */
+int teco_trunk64_supported(int32_t N, int32_t H, int32_t W, int32_t num_layers);
+int teco_trunk64_tc(int32_t N, int32_t H, int32_t W, int32_t num_layers, const void* x_in, void* buf_a, void* buf_b,
+                    const void* wpk_all, const float* bias_all, void* flags, void* stream);
+
 /* Developer hook: when buf != NULL every teco_conv3x3_tc CTA writes clock64() stamps to buf[cta*32 ..] (phase
  * boundaries: start, setup done, halo landed, first/last weight slab landed, MMAs issued, accumulator ready,
  * epilogue done, teardown).  buf must hold gridDim*32 int64.  Pass NULL to switch it off. */

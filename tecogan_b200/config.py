@@ -1,5 +1,5 @@
 """Run-time configuration of the compute path (not part of the reference interface)."""
-_cfg = {"precision": "bf16", "train_precision": "fp32"}
+_cfg = {"precision": "bf16", "train_precision": "fp32", "fused_trunk": False}
 
 
 def set_precision(p):
@@ -27,3 +27,14 @@ def set_train_precision(p):
 
 def train_precision():
     return _cfg["train_precision"]
+
+
+def set_fused_trunk(on):
+    """Use the one-launch fused generator trunk (teco_trunk64_tc) when the frame is a single wave of tiles.
+    Off by default: bit-identical to the per-layer path but measured 252 us vs 215 us for the 33-layer 128x128 trunk
+    (profiles/conv_tc_r01_notes.md: the neighbour hand-shake runs at the pace of the slowest of nine tiles)."""
+    _cfg["fused_trunk"] = bool(on)
+
+
+def fused_trunk():
+    return _cfg["fused_trunk"]

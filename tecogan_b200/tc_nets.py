@@ -9,6 +9,7 @@ import ctypes
 
 import torch
 
+from . import config
 from . import kernels as K
 from ._ffi import ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH24, call, ptr, stream_ptr
 from .variables import current_scope, default_store
@@ -125,15 +126,28 @@ class GeneratorPlan:
         self.bic = torch.zeros((B, 4 * h, 4 * w, 3), device=device, dtype=f32)
         self.out = torch.zeros((B, 4 * h, 4 * w, 3), device=device, dtype=f32)
         self.launches = 2 * num_resblock + 5 + 1
+        # fused trunk (input conv + all residual blocks in one launch) when the frame is a single wave of 16x8 tiles
+        from ._ffi import lib
+        self.fused = bool(lib().teco_trunk64_supported(B, h, w, 2 * num_resblock + 1)) and config.fused_trunk()
+        if self.fused:
+            layers = [self.l_in] + [l for pair in self.l_res for l in pair]
+            self.trunk_w = torch.cat([l.wpk for l in layers]).contiguous()
+            self.trunk_b = torch.cat([l.bias for l in layers]).contiguous()
+            self.trunk_flags = torch.zeros(B * ((h + 15) // 16) * ((w + 7) // 8), device=device, dtype=torch.int32)
+            self.launches = 1 + 4 + 1
 
     def run(self, lr_f32, lr_cpitch=3):
         """x_in must already hold the packed input; lr_f32: fp32 tensor whose first 3 channels are LR RGB."""
         B, h, w = self.B, self.h, self.w
         call("teco_bicubic4_f32", ptr(lr_f32, f32), ptr(self.bic, f32), B, h, w, 3, lr_cpitch, stream_ptr())
-        K.conv3x3_tc(self.x_in, self.l_in.wpk, self.l_in.bias, self.a, cout=64, act=ACT_RELU)
-        for c1, c2 in self.l_res:
-            K.conv3x3_tc(self.a, c1.wpk, c1.bias, self.b, cout=64, act=ACT_RELU)
-            K.conv3x3_tc(self.b, c2.wpk, c2.bias, self.a, cout=64, act=ACT_NONE, res=self.a)
+        if self.fused:
+            call("teco_trunk64_tc", B, h, w, 2 * self.nrb + 1, ptr(self.x_in, bf16), ptr(self.a, bf16), ptr(self.b, bf16),
+                 ptr(self.trunk_w, bf16), ptr(self.trunk_b, f32), ptr(self.trunk_flags), stream_ptr())
+        else:
+            K.conv3x3_tc(self.x_in, self.l_in.wpk, self.l_in.bias, self.a, cout=64, act=ACT_RELU)
+            for c1, c2 in self.l_res:
+                K.conv3x3_tc(self.a, c1.wpk, c1.bias, self.b, cout=64, act=ACT_RELU)
+                K.conv3x3_tc(self.b, c2.wpk, c2.bias, self.a, cout=64, act=ACT_NONE, res=self.a)
         K.conv3x3_tc(self.a, self.l_t1.wpk, self.l_t1.bias, self.u1, cout=64, act=ACT_RELU, mode=1)
         K.conv3x3_tc(self.u1, self.l_t2.wpk, self.l_t2.bias, self.u2, cout=64, act=ACT_RELU, mode=1)
         # output stage: conv(64->3) + bicubic_four(LR), then preprocess (*2-1): lib/frvsr.py:79-87
