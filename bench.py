@@ -28,6 +28,7 @@ import torch  # noqa: E402
 LR_H = LR_W = 128
 CLIP_FRAMES = 120
 NUM_RESBLOCK = 16
+LOOKAHEAD = os.environ.get("TECO_BENCH_LOOKAHEAD", "1") != "0"   # fnet of frame t+1 concurrent with generator of frame t
 # algorithmic MACs per LR pixel: generator N=16 + fnet
 MACS_PER_LR_PX = 1420992 + 126720
 RESBLOCK_CONV_FLOP = 2.0 * LR_H * LR_W * 576 * 64      # one 3x3 64->64 layer at 128x128 (the dominant kernel)
@@ -215,13 +216,14 @@ def main():
 
     def run_clip_resident():
         eng.reset()
-        for t in range(CLIP_FRAMES):
-            eng.step(clip_dev[t])
+        for t in range(CLIP_FRAMES):                             # look-ahead: fnet(t, t+1) overlaps generator(t)
+            eng.step(clip_dev[t], next_lr=clip_dev[t + 1] if (LOOKAHEAD and t + 1 < CLIP_FRAMES) else None)
 
     def run_clip_e2e():
         eng.reset()
         for t in range(CLIP_FRAMES):
-            eng.step(clip_host[t])                               # pinned host -> device inside
+            # pinned host -> device inside; with look-ahead frame t+1 is the one uploaded (each frame exactly once)
+            eng.step(clip_host[t], next_lr=clip_host[t + 1] if (LOOKAHEAD and t + 1 < CLIP_FRAMES) else None)
             out_host[t].copy_(eng.out_u8[0], non_blocking=True)  # uint8 HR frame back to pinned host
         torch.cuda.current_stream().synchronize()
 

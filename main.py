@@ -83,10 +83,12 @@ def inference(FLAGS):
     max_iter = len(inference_data.inputs)
     srtime = 0
     print('Frame evaluation starts!!')
+    to_dev = lambda k: torch.from_numpy(np.array([inference_data.inputs[k]]).astype(np.float32)).cuda()
+    nxt = to_dev(0)
     for i in range(max_iter):
-        input_im = torch.from_numpy(np.array([inference_data.inputs[i]]).astype(np.float32))
+        input_im, nxt = nxt, (to_dev(i + 1) if i + 1 < max_iter else None)
         t0 = time.time()
-        out = eng.step(input_im.cuda())
+        out = eng.step(input_im, next_lr=nxt)     # the next frame's flow is estimated while this frame is generated
         torch.cuda.synchronize()
         srtime += time.time() - t0
         if i >= 5:

@@ -26,6 +26,7 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue
 // (one epilogue warp per scheduler is latency-bound: ~1000 clk per 32 channels; two per scheduler halve it).
 #include <cuda.h>
+#include <cstdlib>
 #include <type_traits>
 #include "teco_common.cuh"
 
@@ -175,7 +176,8 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // Persistent and pipelined: a CTA walks tiles c, c+G, c+2G, ... of its Cout split.  The halo ring (HST stages), the
 // weight ring (or the resident layer, loaded once) and AS TMEM accumulator stages let the TMA producer, the MMA
 // issuer and the epilogue warps work on three different tiles at the same time.
-template <int MODE, int TPS, int J, int KS>
+// H1: single halo box per block, horizontal taps as 128-byte descriptor start offsets (see conv_tc_sw.cu)
+template <int MODE, int TPS, int J, int KS, int H1>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -233,9 +235,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   if (threadIdx.x == 0) STAMP(1);
 
   constexpr int nacc = MODE == 1 ? 4 : 1;
-  constexpr int ncopies = MODE == 1 ? 2 : 3;     // horizontal tap offsets that occur (tconv only reads x-1, x)
+  constexpr int ncopies = H1 ? 1 : (MODE == 1 ? 2 : 3);   // horizontal tap offsets that occur (tconv only reads x-1, x)
   constexpr int slabs_per_blk = 9 / TPS;
-  constexpr int row_bytes = 8 * J * 128;         // one box row (8J pixels x 128 B)
+  constexpr int row_bytes = (H1 ? 8 * J + 2 : 8 * J) * 128;   // one box row (pixels x 128 B)
   constexpr uint32_t copy_bytes = (uint32_t)(HALO_ROWS * row_bytes);
   const int slabs_per_tile = slabs_per_blk * p.nblk;
   const uint32_t acc_stage_cols = (uint32_t)(J * nacc * KS * p.Ncta);   // TMEM columns of one accumulator stage
@@ -361,7 +363,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               } else {
                 ry = ky; rx = kx; phase = 0;
               }
-              a_off16[tt] = ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
+              a_off16[tt] = H1 ? ((uint32_t)(rx * 128 + ry * row_bytes)) >> 4
+                               : ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
               acc_idx[tt] = (uint32_t)(phase * KS + (KS > 1 ? tt : 0));
             }
             const uint32_t started_now = started;
@@ -633,7 +636,10 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.Ncta = d->Cout / p.nsplit;
   TECO_CHECK_ARG(nacc * p.Ncta <= 512, "teco_conv3x3_tc: Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
   const size_t tap_bytes = (size_t)p.Ncta * 128;
-  const size_t copy1 = (size_t)HALO_ROWS * 8 * 128;            // one kx-copy of a J = 1 halo stage (18 KB)
+  static const int env_h1 = [] { const char* e = getenv("TECO_TC_H1"); return e ? atoi(e) : 1; }();
+  const int H1 = env_h1 ? 1 : 0;
+  // bytes of one J = 1 halo stage: one 10-pixel-wide box (23 KB, padded to the swizzle atom) or three 8-pixel boxes
+  const size_t stage1 = H1 ? (((size_t)HALO_ROWS * 10 * 128 + 1023) & ~(size_t)1023) : 3 * (size_t)HALO_ROWS * 8 * 128;
   const bool single_wave = tiles1 * p.nsplit <= (long long)sms;
   // Dispatch (same-box A/B, profiles/conv_tc_r01_notes.md): the one-tile-per-CTA kernel is faster for single-wave
   // launches and for the epilogue-heavy transposed conv (two CTAs per SM); this persistent kernel wins multi-wave convs.
@@ -646,7 +652,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     // One tile per CTA, one CTA per SM (e.g. the 128x128 trunk: 128 tiles).  Whole layer resident when it fits: fetched
     // before the dependency wait and multicast over a 4-CTA cluster (measured 6.2 us vs 6.9 us for a ring, 64->64).
     p.HST = p.nblk > 1 ? 2 : 1;
-    const size_t a_total1 = (size_t)p.HST * 3 * copy1;
+    const size_t a_total1 = (size_t)p.HST * stage1;
     if (p.nsplit == 1 && a_total1 + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
       p.mcast = 1; p.TPS = 3; p.WST = 3 * p.nblk;
       p.CS = tiles1 >= 8 ? 4 : 1;
@@ -667,7 +673,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     // allows -- two accumulator stages, so TMA, MMA and epilogue overlap across tiles; the layer's weights stay resident
     // in shared memory for the whole launch when they fit next to two halo stages.
     p.HST = 2;
-    const size_t a_total1 = 2 * 3 * copy1;                     // J = 1: 108 KB
+    const size_t a_total1 = 2 * stage1;
     if (a_total1 + 9 * tap_bytes * p.nblk <= budget && 3 * p.nblk <= MAX_WST) {
       p.mcast = 1; p.TPS = 3; p.WST = 3 * p.nblk;             // resident, loaded once per CTA (no cluster: CS = 1)
     } else if (a_total1 + 2 * 3 * tap_bytes <= budget) {
@@ -685,8 +691,8 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.tiles_x = teco_ceil_div(d->W, 8 * J);
   p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
   p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
-  p.copy_bytes = (uint32_t)(HALO_ROWS * 8 * J * 128);
-  p.halo_stage_bytes = 3 * p.copy_bytes;
+  p.copy_bytes = (uint32_t)(HALO_ROWS * (H1 ? 8 * J + 2 : 8 * J) * 128);
+  p.halo_stage_bytes = H1 ? ((p.copy_bytes + 1023u) & ~1023u) : 3 * p.copy_bytes;
   const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
   p.w_slab_bytes = (uint32_t)(p.TPS * tap_bytes);
   p.KS = (p.TPS == 3 && d->mode == 0 && J * 3 * p.Ncta <= 512) ? 3 : 1;
@@ -707,7 +713,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   CUtensorMap tmap;
   const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
   const cuuint64_t gstr[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(8 * J), (cuuint32_t)HALO_ROWS, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(H1 ? 8 * J + 2 : 8 * J), (cuuint32_t)HALO_ROWS, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -719,7 +725,9 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   }
   using KernelT = void (*)(const CUtensorMap, const TcParams);
   KernelT kern = nullptr;
-#define TECO_PICK(M, T, JJ, K) if (d->mode == M && p.TPS == T && J == JJ && p.KS == K) kern = conv3x3_tc_kernel<M, T, JJ, K>;
+#define TECO_PICK(M, T, JJ, K)                                              \
+  if (d->mode == M && p.TPS == T && J == JJ && p.KS == K)                   \
+    kern = H1 ? conv3x3_tc_kernel<M, T, JJ, K, 1> : conv3x3_tc_kernel<M, T, JJ, K, 0>;
   TECO_PICK(0, 3, 1, 3) TECO_PICK(0, 3, 2, 3) TECO_PICK(0, 3, 1, 1) TECO_PICK(0, 3, 2, 1) TECO_PICK(0, 1, 1, 1) TECO_PICK(0, 1, 2, 1)
   TECO_PICK(1, 3, 1, 1) TECO_PICK(1, 3, 2, 1) TECO_PICK(1, 1, 1, 1) TECO_PICK(1, 1, 2, 1)
 #undef TECO_PICK

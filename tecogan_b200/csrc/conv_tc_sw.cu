@@ -30,6 +30,7 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue
 // (one epilogue warp per scheduler is latency-bound: ~1000 clk per 32 channels; two per scheduler halve it).
 #include <cuda.h>
+#include <cstdlib>
 #include <type_traits>
 #include "teco_common.cuh"
 
@@ -174,7 +175,11 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // MODE 0 conv / 1 transposed conv; TPS taps per weight slab; J sub-tiles per CTA; KS K-split accumulator chains.
 // They are compile-time so that the MMA issue loop is a fully unrolled stream of UTCHMMA whose descriptors differ
 // from per-stage bases by immediates (uniform-datapath adds, no per-instruction R2UR).
-template <int MODE, int TPS, int J, int KS>
+// H1 = 1: ONE halo box (8J+2 pixels wide) per block instead of one box per horizontal tap; the horizontal taps are
+// descriptor start offsets of whole 128-byte pixel rows (not swizzle-atom aligned: the SW128 XOR is a function of the
+// absolute shared-memory address bits, which is also how TMA wrote the box; the descriptor's base-offset field stays 0 --
+// setting it to (addr >> 7) & 7 was tested on the B200 and gives wrong results).  2.4x less L2->smem traffic, 23 KB per stage.
+template <int MODE, int TPS, int J, int KS, int H1>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -234,9 +239,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   if (threadIdx.x == 0) STAMP(1);
 
   constexpr int nacc = MODE == 1 ? 4 : 1;
-  constexpr int ncopies = MODE == 1 ? 2 : 3;     // horizontal tap offsets that occur (tconv only reads x-1, x)
+  constexpr int ncopies = H1 ? 1 : (MODE == 1 ? 2 : 3);   // horizontal tap offsets that occur (tconv only reads x-1, x)
   constexpr int slabs_per_blk = 9 / TPS;
-  constexpr int row_bytes = 8 * J * 128;         // one box row (8J pixels x 128 B)
+  constexpr int row_bytes = (H1 ? 8 * J + 2 : 8 * J) * 128;   // one box row (pixels x 128 B)
   constexpr uint32_t copy_bytes = (uint32_t)(HALO_ROWS * row_bytes);
 
   if (warp == 0) {
@@ -341,7 +346,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             } else {
               ry = ky; rx = kx; phase = 0;
             }
-            a_off16[tt] = ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
+            a_off16[tt] = H1 ? ((uint32_t)(rx * 128 + ry * row_bytes)) >> 4
+                             : ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
             acc_idx[tt] = (uint32_t)(phase * KS + (KS > 1 ? tt : 0));
           }
           const uint32_t started_now = started;
@@ -360,7 +366,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 #pragma unroll
                     for (int t2 = 0; t2 < tt; ++t2) accum |= (acc_idx[t2] == acc_idx[tt]) ? 1u : 0u;
                   }
-                  umma_bf16(tmem_base + acc * (uint32_t)p.Ncta, a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
+                  umma_bf16(tmem_base + acc * (uint32_t)p.Ncta,
+                            a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
                             b_base + tt * tap_stride16 + (uint32_t)((s * 32) >> 4), idesc, accum);
                 }
               }
@@ -536,6 +543,8 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   p.res_f32 = res_f32; p.out_f32 = out_f32; p.dbg = teco_g_dbg_timing;
   p.nblk = d->Cin / CB;
   p.HST = p.nblk > 1 ? 2 : 1;
+  static const int env_h1 = [] { const char* e = getenv("TECO_TC_H1"); return e ? atoi(e) : 1; }();
+  const int H1 = env_h1 ? 1 : 0;
   // few spatial tiles but many output channels (FNet's 16x16 / 32x32 layers): split Cout over CTAs, 64 channels each
   {
     long long t1 = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8);
@@ -550,7 +559,8 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   int J = 1;
   for (int j = 2; j >= 1; --j) {
     if (j * nacc * p.Ncta > 512) continue;
-    size_t a_bytes = (size_t)p.HST * 3 * HALO_ROWS * 8 * j * 128;
+    size_t a_bytes = H1 ? (size_t)p.HST * (((size_t)HALO_ROWS * (8 * j + 2) * 128 + 1023) & ~(size_t)1023)
+                        : (size_t)p.HST * 3 * HALO_ROWS * 8 * j * 128;
     if (a_bytes + 2 * (size_t)p.Ncta * 128 > budget) continue;
     long long tiles = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8 * j);
     if (tiles >= 2LL * sms || j == 1) { J = j; break; }
@@ -559,8 +569,8 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   p.J = J;
   p.tiles_x = teco_ceil_div(d->W, 8 * J);
   p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
-  p.copy_bytes = (uint32_t)(HALO_ROWS * 8 * J * 128);
-  p.halo_stage_bytes = 3 * p.copy_bytes;
+  p.copy_bytes = (uint32_t)(HALO_ROWS * (H1 ? 8 * J + 2 : 8 * J) * 128);
+  p.halo_stage_bytes = H1 ? ((p.copy_bytes + 1023u) & ~1023u) : 3 * p.copy_bytes;
   const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
   const size_t tap_bytes = (size_t)p.Ncta * 128;
   // whole layer resident?  then 3 taps per slab (3 barriers per block), fetched once, multicast over a 4-CTA cluster
@@ -596,7 +606,9 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   uint32_t cols = (uint32_t)(J * nacc * p.KS * p.Ncta), tc = 32;
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
-  const size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float);
+  size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float);
+  static const int env_1cta = [] { const char* e = getenv("TECO_TC_1CTA"); return e ? atoi(e) : 0; }();
+  if (env_1cta && single_wave && smem_bytes < 116 * 1024) smem_bytes = 116 * 1024;   // experiment: forbid two CTAs per SM
 
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -606,7 +618,7 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   CUtensorMap tmap;
   const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
   const cuuint64_t gstr[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(8 * J), (cuuint32_t)HALO_ROWS, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(H1 ? 8 * J + 2 : 8 * J), (cuuint32_t)HALO_ROWS, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -618,7 +630,9 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   }
   using KernelT = void (*)(const CUtensorMap, const TcParams);
   KernelT kern = nullptr;
-#define TECO_PICK(M, T, JJ, K) if (d->mode == M && p.TPS == T && J == JJ && p.KS == K) kern = conv3x3_tc_kernel<M, T, JJ, K>;
+#define TECO_PICK(M, T, JJ, K)                                              \
+  if (d->mode == M && p.TPS == T && J == JJ && p.KS == K)                   \
+    kern = H1 ? conv3x3_tc_kernel<M, T, JJ, K, 1> : conv3x3_tc_kernel<M, T, JJ, K, 0>;
   TECO_PICK(0, 3, 1, 3) TECO_PICK(0, 3, 2, 3) TECO_PICK(0, 3, 1, 1) TECO_PICK(0, 3, 2, 1) TECO_PICK(0, 1, 1, 1) TECO_PICK(0, 1, 2, 1)
   TECO_PICK(1, 3, 1, 1) TECO_PICK(1, 3, 2, 1) TECO_PICK(1, 1, 1, 1) TECO_PICK(1, 1, 2, 1)
 #undef TECO_PICK

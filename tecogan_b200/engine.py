@@ -7,6 +7,11 @@ frame 0 uses pre_warp = 0.
 
 bf16 mode keeps everything in pre-allocated device buffers and replays ONE CUDA graph per frame
 (~57 tcgen05 launches + warp/s2d + resample kernels); fp32 mode runs the differentiable mirror under no_grad.
+
+Look-ahead (bf16 mode, step(lr, next_lr=...) / run_sequence): the flow of frame i+1 depends only on LR_i and LR_{i+1}
+(main.py:211), not on any HR output, so fnet(LR_i ++ LR_{i+1}) is captured on a second stream of the frame graph and
+runs concurrently with generator_F of frame i; frame i+1 then starts directly with warp + generator.  Same kernels on
+the same inputs in the same order per buffer, hence bit-identical outputs to the serial recurrence (tested).
 """
 import torch
 
@@ -37,6 +42,9 @@ class InferenceEngine:
         self.out_u8 = torch.zeros((batch, 4 * h, 4 * w, 3), device=self.device, dtype=torch.uint8)
         self.frame_idx = 0
         self.graph = None
+        self.graph_la = None          # frame graph with the next frame's fnet on a second stream
+        self.graph_tail = None        # frame graph that consumes a precomputed flow, no look-ahead
+        self.flow_ready = False       # self.flow_cur holds fnet(prev_lr ++ lr_in) for the frame about to be processed
         self.launches_per_frame = 0
         if self.precision == "bf16":
             with variable_scope('generator'), variable_scope('generator_unit') as gs:
@@ -46,6 +54,9 @@ class InferenceEngine:
                 _ensure_vars_fnet()
                 self.fnet = FNetPlan(fs, batch, h, w, self.device)
             self.launches_per_frame = self.gen.launches + self.fnet.launches + 6
+            self.lr_next = torch.zeros_like(self.lr_in)
+            self.flow_cur = torch.zeros_like(self.fnet.flow)
+            self._side = torch.cuda.Stream(device=self.device)
         else:
             self.pre_gen = torch.zeros((batch, 4 * h, 4 * w, 3), device=self.device, dtype=f32)
             self.pre_warp = torch.zeros_like(self.pre_gen)
@@ -68,10 +79,47 @@ class InferenceEngine:
         g.run(self.lr_in, 3)
         self._finish()
 
-    def _finish(self):
+    def _finish(self, keep_lr=True):
         n = self.out01.numel()
         call("teco_affine_act_f32", ptr(self.gen.out, f32), ptr(self.out01, f32), n, 0.5, 0.5, 0, stream_ptr())  # deprocess
         call("teco_to_u8", ptr(self.out01, f32), ptr(self.out_u8, torch.uint8), n, stream_ptr())
+        if keep_lr:
+            self.prev_lr.copy_(self.lr_in)
+
+    # -- look-ahead pieces
+    def _fnet_ahead(self):
+        """fnet(LR_i ++ LR_{i+1}) from lr_in / lr_next into self.fnet.flow (current stream)."""
+        f = self.fnet
+        _f32_slice_to_bf16(self.lr_in, 0, 3, f.x_in, 0)
+        _f32_slice_to_bf16(self.lr_next, 0, 3, f.x_in, 3)
+        f.run()
+
+    def _gen_from_flow(self, after_warp=None):
+        g = self.gen
+        K.warp_s2d_fused(g.out, self.flow_cur, g.x_in, S2D_OFF, in_scale=0.5, in_shift=0.5)
+        if after_warp is not None:
+            after_warp.record()
+        _f32_slice_to_bf16(self.lr_in, 0, 3, g.x_in, LR_OFF)
+        g.run(self.lr_in, 3)
+        self._finish(keep_lr=False)
+
+    def _frame_lookahead(self):
+        """Frame i from the precomputed flow on the current stream; fnet for frame i+1 on the side stream."""
+        main, side = torch.cuda.current_stream(), self._side
+        warped = torch.cuda.Event()
+        side.wait_stream(main)                       # fork
+        with torch.cuda.stream(side):
+            self._fnet_ahead()
+        self._gen_from_flow(after_warp=warped)
+        with torch.cuda.stream(side):
+            side.wait_event(warped)                  # flow_cur has been consumed by this frame's warp
+            self.flow_cur.copy_(self.fnet.flow)
+        main.wait_stream(side)                       # join
+        self.prev_lr.copy_(self.lr_in)
+        self.lr_in.copy_(self.lr_next)
+
+    def _frame_tail(self):
+        self._gen_from_flow()
         self.prev_lr.copy_(self.lr_in)
 
     # ------------------------------------------------------------------ fp32 path (exact-parity mode)
@@ -102,51 +150,90 @@ class InferenceEngine:
     # ------------------------------------------------------------------ public API
     def reset(self):
         self.frame_idx = 0
+        self.flow_ready = False
 
-    def step(self, lr=None):
+    def _check_frame(self, lr, what):
+        if lr.dim() == 3:
+            lr = lr.unsqueeze(0)
+        if tuple(lr.shape) != tuple(self.lr_in.shape):
+            raise ValueError("InferenceEngine.step: expected %s of shape %s, got %s"
+                             % (what, tuple(self.lr_in.shape), tuple(lr.shape)))
+        return lr
+
+    def step(self, lr=None, next_lr=None):
         """Advance one frame.  lr: [B,h,w,3] (or [h,w,3] when B == 1) fp32 in [0,1], CUDA or pinned host; if None the
-        caller has already filled self.lr_in.  Returns self.out01 ([B,4h,4w,3] fp32 in [0,1], overwritten each step)."""
-        if lr is not None:
-            if lr.dim() == 3:
-                lr = lr.unsqueeze(0)
-            if tuple(lr.shape) != tuple(self.lr_in.shape):
-                raise ValueError("InferenceEngine.step: expected LR frame of shape %s, got %s"
-                                 % (tuple(self.lr_in.shape), tuple(lr.shape)))
-            self.lr_in.copy_(lr, non_blocking=True)
+        caller has already filled self.lr_in.  Returns self.out01 ([B,4h,4w,3] fp32 in [0,1], overwritten each step).
+
+        next_lr (bf16 mode): the FOLLOWING LR frame.  When given, its flow is computed concurrently with this frame's
+        generator, and the next call starts from that flow; the next call's `lr` must then be this `next_lr` (it is
+        already on the device and is not uploaded again)."""
+        if next_lr is not None and self.precision != "bf16":
+            next_lr = None                       # the fp32 exact-parity mode stays strictly serial
+        pending = self.flow_ready
+        if lr is not None and not pending:
+            self.lr_in.copy_(self._check_frame(lr, "LR frame"), non_blocking=True)
+        if next_lr is not None:
+            self.lr_next.copy_(self._check_frame(next_lr, "next LR frame"), non_blocking=True)
         if self.precision != "bf16":
             self._frame_fp32()
-        elif self.frame_idx == 0:
-            self._frame_first()
+        elif self.frame_idx == 0 or (next_lr is not None and not pending):
+            # first frame of a clip (or look-ahead requested without a pending flow): serial frame, then prime the flow
+            if self.frame_idx == 0:
+                self._frame_first()
+            else:
+                self._frame_next()
+            if next_lr is not None:
+                self._fnet_ahead()
+                self.flow_cur.copy_(self.fnet.flow)
+                self.lr_in.copy_(self.lr_next)
+                self.flow_ready = True
+        elif pending:
+            body = self._frame_lookahead if next_lr is not None else self._frame_tail
+            if not self.use_graph:
+                body()
+            else:
+                attr = "graph_la" if next_lr is not None else "graph_tail"
+                if getattr(self, attr) is None:
+                    setattr(self, attr, self._capture(body))
+                getattr(self, attr).replay()
+            self.flow_ready = next_lr is not None
         elif not self.use_graph:
             self._frame_next()
         else:
             if self.graph is None:
-                self._capture()
+                self.graph = self._capture(self._frame_next)
             self.graph.replay()
         self.frame_idx += 1
         return self.out01
 
-    def _capture(self):
-        # warm-up once eagerly on a side stream (sets function attributes, builds tensor maps), then capture
-        snap = (self.gen.out.clone(), self.prev_lr.clone(), self.gen.x_in.clone())
+    def _capture(self, body):
+        # warm-up once eagerly on a side stream (sets function attributes, builds tensor maps), then capture;
+        # the recurrent state is restored after both passes so that the replay sees the real previous frame
+        state = (self.gen.out, self.prev_lr, self.gen.x_in, self.lr_in, self.lr_next, self.flow_cur, self.fnet.flow)
+        snap = [t.clone() for t in state]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self._frame_next()
+            body()
         torch.cuda.current_stream().wait_stream(s)
-        self.gen.out.copy_(snap[0]); self.prev_lr.copy_(snap[1]); self.gen.x_in.copy_(snap[2])
+        for t, v in zip(state, snap):
+            t.copy_(v)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._frame_next()
-        self.gen.out.copy_(snap[0]); self.prev_lr.copy_(snap[1]); self.gen.x_in.copy_(snap[2])
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        for t, v in zip(state, snap):
+            t.copy_(v)
+        return graph
 
-    def run_sequence(self, frames, out="f32"):
+    def run_sequence(self, frames, out="f32", lookahead=True):
         """frames: iterable of [h,w,3] / [B,h,w,3] tensors.  Returns a list of CUDA tensors, one per frame
         ('f32': [0,1] floats; 'u8': save_img quantisation, reference lib/ops.py:521-523)."""
         self.reset()
         res = []
-        for fr in frames:
-            self.step(fr)
+        frames = list(frames)
+        for i, fr in enumerate(frames):
+            nxt = frames[i + 1] if (lookahead and i + 1 < len(frames)) else None
+            self.step(fr, next_lr=nxt)
             res.append((self.out01 if out == "f32" else self.out_u8).clone())
         return res

@@ -195,3 +195,28 @@ def test_fused_trunk_is_bit_identical_to_per_layer_launches(B, h, w, n):
         assert torch.equal(o, outs[False][0])
     ref = O.generator_F(p, x.cpu(), n)
     assert O.psnr(outs[True][0].cpu().numpy(), ref.numpy(), peak=2.0) > 45.0
+
+
+def test_fnet_lookahead_is_bit_identical_to_the_serial_recurrence():
+    """fnet(LR_i ++ LR_{i+1}) depends on no HR output (reference main.py:211), so the engine may run it concurrently with
+    generator_F of frame i; every mix of look-ahead / serial steps must reproduce the serial outputs bit for bit."""
+    from tecogan_b200 import config
+    from tecogan_b200.engine import InferenceEngine
+    pg, pf = O.damp_generator(O.init_generator(seed=5, num_resblock=3)), O.init_fnet(seed=6)
+    _fresh_store({**pg, **pf})
+    config.set_precision("bf16")
+    g = torch.Generator().manual_seed(11)
+    frames = [torch.rand(32, 48, 3, generator=g).cuda() for _ in range(7)]
+    serial = InferenceEngine(32, 48, 3).run_sequence(frames, lookahead=False)
+    for use_graph in (True, False):
+        ahead = InferenceEngine(32, 48, 3, use_graph=use_graph).run_sequence(frames, lookahead=True)
+        for a, b in zip(ahead, serial):
+            assert torch.equal(a, b)
+    # mixed: serial, serial, look-ahead primed mid-clip, look-ahead, tail (no next frame), serial again
+    eng = InferenceEngine(32, 48, 3)
+    plan = [None, None, 3, 4, None, None, None]
+    for i, fr in enumerate(frames):
+        out = eng.step(fr, next_lr=frames[plan[i]] if plan[i] is not None else None)
+        assert torch.equal(out, serial[i]), i
+    with pytest.raises(ValueError):
+        eng.step(frames[0], next_lr=torch.zeros(8, 8, 3, device="cuda"))
