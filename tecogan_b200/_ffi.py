@@ -65,6 +65,7 @@ SIGNATURES = {
     "teco_bf16_to_f32_add": [_P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "teco_f32_to_bf16_rowpad": [_P, _P, _I64, _I32, _I32, _I32, _P],
     "teco_to_u8": [_P, _P, _I64, _P],
+    "teco_deprocess_u8": [_P, _P, _P, _I64, _P],
     "teco_bn_train_f32": [_P, _P, _P, _P, _I64, _I32, _F, _I32, _P],
     "teco_bn_train_bwd_f32": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _P],
     "teco_loss_l2_f32": [_P, _P, _P, _P, _I64, _I32, _F, _P],

@@ -49,6 +49,7 @@ struct TcParams {
   int nblk, WST, TPS, KS;              // Cin/64, weight ring stages, taps per weight slab (1 or 3), K-split chains
   int HST, CS, mcast, num_tiles;       // halo stages, cluster size, resident+multicast weights, real tile count
   uint32_t copy_bytes, halo_stage_bytes, w_slab_bytes, tmem_cols;
+  int tma_out, tma_res;                // staged epilogue: bf16 output / residual tiles through swizzled smem + TMA (see conv_tc_sw.cu)
   const uint8_t* wpk;
   const float* bias;
   const __nv_bfloat16* res;
@@ -92,6 +93,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -179,7 +189,8 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // H1: single halo box per block, horizontal taps as 128-byte descriptor start offsets (see conv_tc_sw.cu)
 template <int MODE, int TPS, int J, int KS, int H1>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
+                  const __grid_constant__ CUtensorMap tmap_r, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,13 +206,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(acc_empty + 3);   // [Ncta]
+  uint64_t* res_full = acc_empty + 3 + 128;      // after 256 floats of bias
+  uint64_t* res_empty = res_full + 1;
+  // output / residual staging tiles: J x [128 pixels][128 B], SWIZZLE_128B image of the TMA box (64 ch, 8 px, 16 rows)
+  uint8_t* stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(res_empty + 2) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_res = stage_out + (size_t)J * 16384;
 
   // work assignment: grid = nsplit x G CTAs; CTA c of a split owns tiles c, c+G, ...
   const int c_in_split = blockIdx.x % p.G;
   const int n0 = (blockIdx.x / p.G) * p.Ncta;   // first output channel of this CTA (all CTAs of a cluster share it)
   const int my_tiles = c_in_split < p.num_tiles ? (p.num_tiles - c_in_split + p.G - 1) / p.G : 0;
-  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;   // [0,32) phase stamps, [32,64) per-tile stamps
 #define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+#define TSTAMP(it, i) do { if (dbg && (it) < 8) dbg[32 + (it) * 4 + (i)] = clock64(); } while (0)
   if (threadIdx.x == 0) STAMP(0);
 
   if (threadIdx.x == 0) {
@@ -217,8 +234,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), NUM_EPI_WARPS);
     }
+    mbar_init(smem_u32(res_full), 1);
+    mbar_init(smem_u32(res_empty), NUM_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_y) : "memory");
+    if (p.tma_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_r) : "memory");
   }
   if (warp == 1) {  // TMEM allocation (one full warp), result lands in smem
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -309,6 +330,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         __syncwarp();
         if (++hs == p.HST) { hs = 0; hph ^= 1; }
       }
+      if (p.tma_res) {   // residual tile(s) of this output tile, after its halo so that the halo prefetch never waits on the epilogue: free once the epilogue of the previous tile has read them
+        if (lane == 0) {
+          mbar_wait(smem_u32(res_empty), (uint32_t)((it & 1) ^ 1));
+          mbar_expect_tx(smem_u32(res_full), (uint32_t)(J * 16384));
+        }
+        __syncwarp();
+        if (lane < J) tma_load_4d(smem_u32(stage_res + (size_t)lane * 16384), &tmap_r, smem_u32(res_full), n0, x0 + 8 * lane, y0, n);
+      }
     }
     if (my_tiles == 0 && p.mcast && lane == 0) {
       // padding CTA of a cluster: it only relays its share of the weights; stay until they have landed here too
@@ -333,6 +362,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         mbar_wait_warp(smem_u32(&halo_full[hs]), hph);
         tcgen05_fence_after();
         if (lane == 0 && b == 0 && it == 0) STAMP(2);
+        if (lane == 0 && b == 0) TSTAMP(it, 0);
         const uint32_t halo_addr = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
         for (int g = 0; g < slabs_per_blk; ++g) {
           if (p.mcast) {   // resident: slab index is fixed, the barrier completes exactly once
@@ -365,24 +395,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               }
               a_off16[tt] = H1 ? ((uint32_t)(rx * 128 + ry * row_bytes)) >> 4
                                : ((uint32_t)rx * copy_bytes + (uint32_t)(ry * row_bytes)) >> 4;
-              acc_idx[tt] = (uint32_t)(phase * KS + (KS > 1 ? tt : 0));
+              acc_idx[tt] = (uint32_t)(phase * KS);   // first chain of this tap's accumulator
             }
+            // K-split chain of an MMA: KS == 3 -> the tap within the slab (kx), KS == 2 -> parity of the k-step.
+            // Order k-step, tap, sub-tile: consecutive MMAs hit J x KS different accumulators (dependent MMAs on one
+            // accumulator cost ~125 cycles each; 3 chains ~72, 6 chains ~59: profiles/conv_tc_r01_notes.md).
             const uint32_t started_now = started;
+            uint32_t touched = 0;
+#pragma unroll
+            for (int s = 0; s < CB / 16; ++s)
+#pragma unroll
+              for (int tt = 0; tt < TPS; ++tt)
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                  touched |= 1u << ((uint32_t)(j * nacc * KS) + acc_idx[tt] + (uint32_t)(KS == 3 ? tt : (KS == 2 ? (s & 1) : 0)));
             if (elect_one()) {
-              // order: sub-tile, k-step, tap -> consecutive MMAs hit different accumulators when KS > 1 / MODE == 1
+              uint32_t seen = started_now;   // accumulators written so far (this tile); folds to constants when unrolled
 #pragma unroll
-              for (int j = 0; j < J; ++j) {
+              for (int s = 0; s < CB / 16; ++s) {
 #pragma unroll
-                for (int s = 0; s < CB / 16; ++s) {
+                for (int tt = 0; tt < TPS; ++tt) {
 #pragma unroll
-                  for (int tt = 0; tt < TPS; ++tt) {
-                    const uint32_t acc = (uint32_t)(j * nacc * KS) + acc_idx[tt];
-                    uint32_t accum = 1u;
-                    if (s == 0) {   // first k-step of this slab: overwrite only if nobody has written this accumulator yet
-                      accum = (started_now >> acc) & 1u;
-#pragma unroll
-                      for (int t2 = 0; t2 < tt; ++t2) accum |= (acc_idx[t2] == acc_idx[tt]) ? 1u : 0u;
-                    }
+                  for (int j = 0; j < J; ++j) {
+                    const uint32_t acc = (uint32_t)(j * nacc * KS) + acc_idx[tt] + (uint32_t)(KS == 3 ? tt : (KS == 2 ? (s & 1) : 0));
+                    const uint32_t accum = (seen >> acc) & 1u;
+                    seen |= 1u << acc;
                     umma_bf16(tmem_acc + acc * (uint32_t)p.Ncta, a_base + a_off16[tt] + (uint32_t)((j * 1024 + s * 32) >> 4),
                               b_base + tt * tap_stride16 + (uint32_t)((s * 32) >> 4), idesc, accum);
                   }
@@ -390,10 +427,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               }
             }
             __syncwarp();
-#pragma unroll
-            for (int j = 0; j < J; ++j)
-#pragma unroll
-              for (int tt = 0; tt < TPS; ++tt) started |= 1u << ((uint32_t)(j * nacc * KS) + acc_idx[tt]);
+            started |= touched;
             if (!p.mcast && elect_one()) tcgen05_commit(smem_u32(&w_empty[ws]));  // frees the slab when these MMAs retire
           }
           __syncwarp();
@@ -405,6 +439,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
       if (elect_one()) tcgen05_commit(smem_u32(&acc_full[as]));
       if (lane == 0 && it == 0) STAMP(5);
+      if (lane == 0) TSTAMP(it, 1);
       __syncwarp();
     }
   } else {
@@ -429,6 +464,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         mbar_wait_warp(smem_u32(&acc_full[as]), ause & 1u);
         tcgen05_fence_after();
         if (threadIdx.x == 64 && it == 0) STAMP(6);
+        if (threadIdx.x == 64) TSTAMP(it, 2);
         const uint32_t tmem_acc = tmem_base + (uint32_t)as * acc_stage_cols;
         const int oy_in = y0 + ry;
         for (int j = 0; j < J; ++j) {
@@ -447,7 +483,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               uint32_t r[EW];
               __syncwarp();
               if (EW == 32) tmem_ld32(tcol + (uint32_t)c0, r); else tmem_ld16(tcol + (uint32_t)c0, r);
-              if (KS == 3) {   // K-split chains: issue all three TMEM loads, wait once, add
+              if (KS == 3) {   // K-split chains: issue all the TMEM loads, wait once, add
                 uint32_t r2[EW], r3[EW];
                 if (EW == 32) { tmem_ld32(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld32(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
                 else { tmem_ld16(tcol + (uint32_t)(p.Ncta + c0), r2); tmem_ld16(tcol + (uint32_t)(2 * p.Ncta + c0), r3); }
@@ -455,6 +491,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 #pragma unroll
                 for (int i = 0; i < EW; ++i)
                   r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]) + __uint_as_float(r3[i]));
+              } else if (KS == 2) {
+                uint32_t r2[EW];
+                if (EW == 32) tmem_ld32(tcol + (uint32_t)(p.Ncta + c0), r2); else tmem_ld16(tcol + (uint32_t)(p.Ncta + c0), r2);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < EW; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
               } else {
                 tmem_wait_ld();
               }
@@ -473,6 +515,47 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop; rare (FNet head): keep it rolled
 #pragma unroll 1
                 for (int i = 0; i < EW; ++i) v[i] = teco_act(v[i], p.act);
+              }
+              if (MODE == 0 && EW == 32 && p.tma_out) {
+                // c0 == 32 * chalf (Ncta == 64).  Pixel m owns row m of the staging tile; its 64 B are chunks 4*chalf..+3,
+                // XOR-swizzled with (m & 7) exactly like the TMA box -> conflict-free 16-byte accesses.
+                const uint32_t rowoff = (uint32_t)m * 128u;
+                if (j == 0) {
+                  // the previous tile's TMA store has finished reading the staging buffer (thread 64 waited before arriving)
+                  if (threadIdx.x == 64) bulk_wait_read();
+                  asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+                  if (p.tma_res) mbar_wait_warp(smem_u32(res_full), (uint32_t)(it & 1));
+                }
+                if (p.tma_res) {
+                  const uint8_t* rs = stage_res + (size_t)j * 16384 + rowoff;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(rs + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4));
+                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+                      v[8 * k + 2 * i] += f.x;
+                      v[8 * k + 2 * i + 1] += f.y;
+                    }
+                  }
+                  if (j == J - 1) {
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(res_empty)) : "memory");
+                  }
+                }
+                uint8_t* os = stage_out + (size_t)j * 16384 + rowoff;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  uint32_t o[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                    o[i] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  *reinterpret_cast<uint4*>(os + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                continue;
               }
               if (!in_img) continue;
               if (p.out_f32) {
@@ -516,6 +599,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             }
           }
         }
+        if (MODE == 0 && EW == 32 && p.tma_out) {
+          fence_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+          if (threadIdx.x == 64) {
+            for (int j = 0; j < J; ++j) tma_store_4d(&tmap_y, smem_u32(stage_out + (size_t)j * 16384), n0, x0 + 8 * j, y0, n);
+            bulk_commit();
+          }
+        }
+        if (threadIdx.x == 64) TSTAMP(it, 3);
         // warps with no channel step of their own (16-channel output stage: chalf == 1) still release the stage
         if (chalf * EW >= p.Ncta) {
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
@@ -524,6 +616,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     };
     if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});   // (a single EW = 16 instantiation halves the SASS but
     else run(std::integral_constant<int, 16>{});                   //  measured 7.4 us vs 6.9 us on the 64->64 layer)
+    if (p.tma_out && threadIdx.x == 64) bulk_wait_all();           // all output tiles are written before the CTA retires
   }
 
   if (threadIdx.x == 64) STAMP(7);
@@ -687,6 +780,16 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
       p.WST = wst;
     }
   }
+  // Multi-wave 3x3 convs with <= 64 output channels per CTA: two 16x8 sub-tiles per tile and two K-split chains each
+  // (4 independent accumulators) instead of one sub-tile with three -- a third less TMEM read traffic in the epilogue
+  // (the 64 B/clk tcgen05.ld path bounds it) and a 16+2 pixel wide halo row instead of two 8+2 ones.
+  static const int env_j2 = [] { const char* e = getenv("TECO_TC_J2"); return e ? atoi(e) : 1; }();
+  int ks_force = 0;
+  if (!single_wave && H1 && env_j2 && d->mode == 0 && p.TPS == 3 && p.mcast && p.Ncta <= 64 &&
+      tiles1 >= 4LL * sms) {
+    const size_t stage2 = ((size_t)HALO_ROWS * 18 * 128 + 1023) & ~(size_t)1023;
+    if (2 * stage2 + 9 * tap_bytes * p.nblk <= budget) { J = 2; ks_force = 2; }
+  }
   p.J = J;
   p.tiles_x = teco_ceil_div(d->W, 8 * J);
   p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
@@ -695,7 +798,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.halo_stage_bytes = H1 ? ((p.copy_bytes + 1023u) & ~1023u) : 3 * p.copy_bytes;
   const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
   p.w_slab_bytes = (uint32_t)(p.TPS * tap_bytes);
-  p.KS = (p.TPS == 3 && d->mode == 0 && J * 3 * p.Ncta <= 512) ? 3 : 1;
+  p.KS = ks_force ? ks_force : ((p.TPS == 3 && d->mode == 0 && J * 3 * p.Ncta <= 512) ? 3 : 1);
   const uint32_t stage_cols = (uint32_t)(J * nacc * p.KS * p.Ncta);
   if (!single_wave && 2 * stage_cols <= 512) p.AS = 2;
   uint32_t cols = stage_cols * (uint32_t)p.AS, tc = 32;
@@ -703,7 +806,15 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.tmem_cols = tc;
   if (single_wave) p.G = (p.num_tiles + p.CS - 1) / p.CS * p.CS;   // padded to the cluster size
   else p.G = p.num_tiles < sms ? p.num_tiles : sms;
-  const size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 4 + 1) * 8 + 256 * sizeof(float);
+  static const int env_tma = [] { const char* e = getenv("TECO_TC_TMA_EPI"); return e ? atoi(e) : 1; }();
+  p.tma_out = (env_tma && d->mode == 0 && y && !out_f32 && p.Ncta == 64) ? 1 : 0;
+  p.tma_res = (p.tma_out && res) ? 1 : 0;
+  size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 4 + 1) * 8 + 256 * sizeof(float) + 32 +
+                      (p.tma_out ? 1024 + (size_t)(1 + p.tma_res) * J * 16384 : 0);
+  if (smem_bytes > 226 * 1024 && p.tma_out) {   // no room for the staging tiles next to this configuration: direct stores
+    smem_bytes -= 1024 + (size_t)(1 + p.tma_res) * J * 16384;
+    p.tma_out = p.tma_res = 0;
+  }
 
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -723,12 +834,28 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
                    d->H, d->W, d->Cin);
     return TECO_E_CUDA;
   }
-  using KernelT = void (*)(const CUtensorMap, const TcParams);
+  CUtensorMap tmap_y = tmap, tmap_r = tmap;   // placeholders when the staged epilogue is off
+  if (p.tma_out) {
+    const cuuint64_t odim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    const cuuint64_t ostr[3] = {(cuuint64_t)d->Cout * 2, (cuuint64_t)d->W * d->Cout * 2, (cuuint64_t)d->H * d->W * d->Cout * 2};
+    const cuuint32_t obox[4] = {64, 8, (cuuint32_t)TILE_ROWS, 1};
+    cr = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS && p.tma_res)
+      cr = enc(&tmap_r, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(res), odim, ostr, obox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      teco_set_error("teco_conv3x3_tc: cuTensorMapEncodeTiled (output tile) failed with CUresult %d", (int)cr);
+      return TECO_E_CUDA;
+    }
+  }
+  using KernelT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
   KernelT kern = nullptr;
 #define TECO_PICK(M, T, JJ, K)                                              \
   if (d->mode == M && p.TPS == T && J == JJ && p.KS == K)                   \
     kern = H1 ? conv3x3_tc_kernel<M, T, JJ, K, 1> : conv3x3_tc_kernel<M, T, JJ, K, 0>;
-  TECO_PICK(0, 3, 1, 3) TECO_PICK(0, 3, 2, 3) TECO_PICK(0, 3, 1, 1) TECO_PICK(0, 3, 2, 1) TECO_PICK(0, 1, 1, 1) TECO_PICK(0, 1, 2, 1)
+  TECO_PICK(0, 3, 2, 2) TECO_PICK(0, 3, 1, 3) TECO_PICK(0, 3, 2, 3) TECO_PICK(0, 3, 1, 1) TECO_PICK(0, 3, 2, 1) TECO_PICK(0, 1, 1, 1) TECO_PICK(0, 1, 2, 1)
   TECO_PICK(1, 3, 1, 1) TECO_PICK(1, 3, 2, 1) TECO_PICK(1, 1, 1, 1) TECO_PICK(1, 1, 2, 1)
 #undef TECO_PICK
   if (!kern) {
@@ -756,7 +883,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_y, tmap_r, p);
   if (le != cudaSuccess) {
     teco_set_error("teco_conv3x3_tc: launch failed: %s (grid %u, cluster %d, smem %zu)", cudaGetErrorString(le), ctas, p.CS, smem_bytes);
     return TECO_E_CUDA;

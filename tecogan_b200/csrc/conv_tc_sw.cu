@@ -51,6 +51,8 @@ struct TcParams {
   float post_scale, post_shift;
   int nblk, WST, TPS, KS;              // Cin/64, weight ring stages, taps per weight slab (1 or 3), K-split chains
   int HST, CS, mcast, num_tiles;       // halo stages, cluster size, resident+multicast weights, real tile count
+  int late_trigger;                    // trigger the dependent launch after the MMAs instead of after the prologue
+  int tma_out, tma_res;                // bf16 output / residual tiles travel through swizzled smem staging + TMA (Ncta == 64, conv)
   uint32_t copy_bytes, halo_stage_bytes, w_slab_bytes, tmem_cols;
   const uint8_t* wpk;
   const float* bias;
@@ -95,6 +97,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// smem tile -> global through the tensor map (clips at the image border); completion tracked by bulk async-groups
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -181,14 +192,22 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // setting it to (addr >> 7) & 7 was tested on the B200 and gives wrong results).  2.4x less L2->smem traffic, 23 KB per stage.
 template <int MODE, int TPS, int J, int KS, int H1>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
+                  const __grid_constant__ CUtensorMap tmap_r, const TcParams p) {
+  // SWIZZLE_128B needs 1024-byte aligned tiles; the dynamic window starts on such a boundary (no static shared memory in
+  // this kernel) -- relied upon instead of a 1 KB slack so that two trunk-layer CTAs (112.3 KB each) share an SM.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   uint8_t* halo_base = smem;                                             // HST stages x 3 kx-copies
   uint8_t* w_base = smem + (size_t)p.HST * p.halo_stage_bytes;           // WST weight slabs
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)p.WST * p.w_slab_bytes);
+  // residual staging tiles (J x 16 KB, TMA box image) follow the weights; the OUTPUT staging tiles reuse the halo
+  // stages, which are dead once the accumulators are complete
+  uint8_t* stage_res = w_base + (size_t)p.WST * p.w_slab_bytes;
+  uint8_t* stage_out = halo_base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_res + (p.tma_res ? (size_t)J * 16384 : 0));
   uint64_t* halo_full = bars;
   uint64_t* halo_empty = bars + 2;
   uint64_t* w_full = bars + 4;
@@ -196,6 +215,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint64_t* acc_full = bars + 4 + 2 * MAX_WST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * MAX_WST + 1);
   float* s_bias = reinterpret_cast<float*>(bars + 4 + 2 * MAX_WST + 2);   // [Cout]
+  uint64_t* res_full = bars + 4 + 2 * MAX_WST + 2 + 128;                  // after 256 floats of bias
 
   // tile coordinates
   int tile = blockIdx.x % p.tiles_pad;      // grid = nsplit x (tiles padded to a multiple of the cluster size)
@@ -221,8 +241,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       mbar_init(smem_u32(&w_empty[i]), 1);
     }
     mbar_init(smem_u32(acc_full), 1);
+    mbar_init(smem_u32(res_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_y) : "memory");
+    if (p.tma_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_r) : "memory");
   }
   if (warp == 1) {  // TMEM allocation (one full warp), result lands in smem
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -234,7 +257,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   if (p.CS > 1) cluster_sync_all();   // every CTA's mbarriers are initialised before any multicast may signal them
   else __syncthreads();
   tcgen05_fence_after();
-  pdl_launch_dependents();
+  // Programmatic dependent launch is triggered LATE (when this CTA's MMAs have been issued, see the MMA warp): the next
+  // layer's CTAs then share the SM only with this layer's epilogue, run their prologue + weight fetch under it, and never
+  // pile up three layers deep (an early trigger let 2 CTAs of later layers land on the 20 idle SMs: 7.45 vs 6.5 us/layer).
+  if (!active || !p.late_trigger) pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) STAMP(1);
 
@@ -279,6 +305,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     if (lane == 0) STAMP(9);
     pdl_wait();   // the previous kernel's output (our input x) is complete and visible from here on
     if (lane == 0) STAMP(10);
+    if (active && p.tma_res) {   // the residual tile (same box as the output tile) lands long before the epilogue needs it
+      if (lane == 0) mbar_expect_tx(smem_u32(res_full), (uint32_t)(J * 16384));
+      __syncwarp();
+      if (lane < J) tma_load_4d(smem_u32(stage_res + (size_t)lane * 16384), &tmap_r, smem_u32(res_full), n0, x0 + 8 * lane, y0, n);
+    }
     if (active) {
       int hs = 0;
       uint32_t hph = 0;
@@ -352,13 +383,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           }
           const uint32_t started_now = started;
           if (elect_one()) {
-            // order: sub-tile, k-step, tap -> consecutive MMAs hit different accumulators when KS > 1 / MODE == 1
+            // order: k-step, tap, sub-tile -> consecutive MMAs hit different accumulators (J sub-tiles x KS chains)
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
+            for (int s = 0; s < CB / 16; ++s) {
 #pragma unroll
-              for (int s = 0; s < CB / 16; ++s) {
+              for (int tt = 0; tt < TPS; ++tt) {
 #pragma unroll
-                for (int tt = 0; tt < TPS; ++tt) {
+                for (int j = 0; j < J; ++j) {
                   const uint32_t acc = (uint32_t)(j * nacc * KS) + acc_idx[tt];
                   uint32_t accum = 1u;
                   if (s == 0) {   // first k-step of this slab: overwrite only if nobody has written this accumulator yet
@@ -388,6 +419,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       if (++hs == p.HST) { hs = 0; hph ^= 1; }
     }
     if (elect_one()) tcgen05_commit(smem_u32(acc_full));
+    if (p.late_trigger) pdl_launch_dependents();
     if (lane == 0) STAMP(5);
     __syncwarp();
   } else if (warp >= 2 && active) {
@@ -446,6 +478,38 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 #pragma unroll
               for (int i = 0; i < EW; ++i) v[i] = teco_act(v[i], p.act);
             }
+            if (MODE == 0 && EW == 32 && p.tma_out) {
+              // c0 == 32 * chalf here (Ncta == 64).  Pixel m owns row m of the staging tile; its 64 B are chunks 4*chalf..+3,
+              // XOR-swizzled with (m & 7) exactly like the TMA box -> conflict-free 16-byte accesses.
+              const uint32_t rowoff = (uint32_t)m * 128u;
+              if (p.tma_res) {
+                mbar_wait_warp(smem_u32(res_full), 0);
+                const uint8_t* rs = stage_res + (size_t)j * 16384 + rowoff;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(rs + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4));
+                  const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+                    v[8 * k + 2 * i] += f.x;
+                    v[8 * k + 2 * i + 1] += f.y;
+                  }
+                }
+              }
+              uint8_t* os = stage_out + (size_t)j * 16384 + rowoff;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                  o[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(os + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+              continue;
+            }
             if (!in_img) continue;
             if (p.out_f32) {
               for (int i = 0; i < EW; ++i) {
@@ -490,6 +554,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     };
     if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});
     else run(std::integral_constant<int, 16>{});
+    if (MODE == 0 && p.tma_out) {
+      // generic-proxy smem writes -> visible to the async proxy, all epilogue warps done, then one thread stores the tiles
+      fence_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+      if (threadIdx.x == 64) {
+        for (int j = 0; j < J; ++j) tma_store_4d(&tmap_y, smem_u32(stage_out + (size_t)j * 16384), n0, x0 + 8 * j, y0, n);
+        bulk_commit();
+        bulk_wait_all();      // the writes are complete before this CTA (and with it the grid) can be considered finished
+      }
+    }
   }
 
   if (threadIdx.x == 64) STAMP(7);
@@ -563,7 +637,8 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
                         : (size_t)p.HST * 3 * HALO_ROWS * 8 * j * 128;
     if (a_bytes + 2 * (size_t)p.Ncta * 128 > budget) continue;
     long long tiles = (long long)d->N * teco_ceil_div(d->H, TILE_ROWS) * teco_ceil_div(d->W, 8 * j);
-    if (tiles >= 2LL * sms || j == 1) { J = j; break; }
+    static const int env_j = [] { const char* e = getenv("TECO_TC_J"); return e ? atoi(e) : 0; }();
+    if (tiles >= 2LL * sms || j == 1 || j == env_j) { J = j; break; }
   }
   TECO_CHECK_ARG(J * nacc * p.Ncta <= 512, "teco_conv3x3_tc(one-tile): Cout=%d too large for mode %d (TMEM has 512 columns)", d->Cout, d->mode);
   p.J = J;
@@ -606,10 +681,14 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   uint32_t cols = (uint32_t)(J * nacc * p.KS * p.Ncta), tc = 32;
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
-  size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float);
-  static const int env_1cta = [] { const char* e = getenv("TECO_TC_1CTA"); return e ? atoi(e) : 0; }();
-  if (env_1cta && single_wave && smem_bytes < 116 * 1024) smem_bytes = 116 * 1024;   // experiment: forbid two CTAs per SM
-
+  static const int env_tma = [] { const char* e = getenv("TECO_TC_TMA_EPI"); return e ? atoi(e) : 1; }();
+  p.tma_out = (env_tma && d->mode == 0 && y && !out_f32 && p.Ncta == 64) ? 1 : 0;
+  p.tma_res = (p.tma_out && res) ? 1 : 0;
+  TECO_CHECK_ARG(!p.tma_out || (size_t)J * 16384 <= a_total, "teco_conv3x3_tc(one-tile): output staging does not fit the halo stages");
+  const size_t smem_bytes = a_total + (size_t)p.WST * p.w_slab_bytes + (p.tma_res ? (size_t)J * 16384 : 0) +
+                            (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float) + 16;
+  static const int env_late = [] { const char* e = getenv("TECO_TC_LATE_TRIGGER"); return e ? atoi(e) : 1; }();
+  p.late_trigger = (env_late && 2 * (smem_bytes + 1024) <= 228 * 1024) ? 1 : 0;   // only useful when two CTAs fit an SM
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     teco_set_error("teco_conv3x3_tc(one-tile): cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -628,7 +707,23 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
                    d->H, d->W, d->Cin);
     return TECO_E_CUDA;
   }
-  using KernelT = void (*)(const CUtensorMap, const TcParams);
+  CUtensorMap tmap_y = tmap, tmap_r = tmap;   // placeholders when the staged epilogue is off
+  if (p.tma_out) {
+    const cuuint64_t odim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    const cuuint64_t ostr[3] = {(cuuint64_t)d->Cout * 2, (cuuint64_t)d->W * d->Cout * 2, (cuuint64_t)d->H * d->W * d->Cout * 2};
+    const cuuint32_t obox[4] = {64, 8, (cuuint32_t)TILE_ROWS, 1};
+    cr = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS && p.tma_res)
+      cr = enc(&tmap_r, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(res), odim, ostr, obox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      teco_set_error("teco_conv3x3_tc(one-tile): cuTensorMapEncodeTiled (output tile) failed with CUresult %d", (int)cr);
+      return TECO_E_CUDA;
+    }
+  }
+  using KernelT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
   KernelT kern = nullptr;
 #define TECO_PICK(M, T, JJ, K)                                              \
   if (d->mode == M && p.TPS == T && J == JJ && p.KS == K)                   \
@@ -662,7 +757,7 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_y, tmap_r, p);
   if (le != cudaSuccess) {
     teco_set_error("teco_conv3x3_tc(one-tile): launch failed: %s (grid %u, cluster %d, smem %zu)", cudaGetErrorString(le), ctas, p.CS, smem_bytes);
     return TECO_E_CUDA;

@@ -53,7 +53,7 @@ class InferenceEngine:
             with variable_scope('fnet'), variable_scope('autoencode_unit') as fs:
                 _ensure_vars_fnet()
                 self.fnet = FNetPlan(fs, batch, h, w, self.device)
-            self.launches_per_frame = self.gen.launches + self.fnet.launches + 6
+            self.launches_per_frame = self.gen.launches + self.fnet.launches + 5
             self.lr_next = torch.zeros_like(self.lr_in)
             self.flow_cur = torch.zeros_like(self.fnet.flow)
             self._side = torch.cuda.Stream(device=self.device)
@@ -81,8 +81,7 @@ class InferenceEngine:
 
     def _finish(self, keep_lr=True):
         n = self.out01.numel()
-        call("teco_affine_act_f32", ptr(self.gen.out, f32), ptr(self.out01, f32), n, 0.5, 0.5, 0, stream_ptr())  # deprocess
-        call("teco_to_u8", ptr(self.out01, f32), ptr(self.out_u8, torch.uint8), n, stream_ptr())
+        call("teco_deprocess_u8", ptr(self.gen.out, f32), ptr(self.out01, f32), ptr(self.out_u8, torch.uint8), n, stream_ptr())
         if keep_lr:
             self.prev_lr.copy_(self.lr_in)
 
@@ -94,23 +93,31 @@ class InferenceEngine:
         _f32_slice_to_bf16(self.lr_next, 0, 3, f.x_in, 3)
         f.run()
 
-    def _gen_from_flow(self, after_warp=None):
+    def _gen_from_flow(self, after_warp=None, lr_ready=None):
         g = self.gen
         K.warp_s2d_fused(g.out, self.flow_cur, g.x_in, S2D_OFF, in_scale=0.5, in_shift=0.5)
         if after_warp is not None:
             after_warp.record()
-        _f32_slice_to_bf16(self.lr_in, 0, 3, g.x_in, LR_OFF)
-        g.run(self.lr_in, 3)
+        if lr_ready is None:
+            _f32_slice_to_bf16(self.lr_in, 0, 3, g.x_in, LR_OFF)
+        else:
+            torch.cuda.current_stream().wait_event(lr_ready)   # LR channels of x_in and bicubic(LR) came from the side stream
+        g.run(self.lr_in, 3, bicubic=lr_ready is None)
         self._finish(keep_lr=False)
 
     def _frame_lookahead(self):
         """Frame i from the precomputed flow on the current stream; fnet for frame i+1 on the side stream."""
         main, side = torch.cuda.current_stream(), self._side
-        warped = torch.cuda.Event()
+        warped, lr_ready = torch.cuda.Event(), torch.cuda.Event()
         side.wait_stream(main)                       # fork
         with torch.cuda.stream(side):
+            # the LR-only parts of this frame's generator leave the critical path too (disjoint channels of x_in
+            # from the warp's space-to-depth channels)
+            _f32_slice_to_bf16(self.lr_in, 0, 3, self.gen.x_in, LR_OFF)
+            self.gen.run_bicubic(self.lr_in, 3)
+            lr_ready.record()
             self._fnet_ahead()
-        self._gen_from_flow(after_warp=warped)
+        self._gen_from_flow(after_warp=warped, lr_ready=lr_ready)
         with torch.cuda.stream(side):
             side.wait_event(warped)                  # flow_cur has been consumed by this frame's warp
             self.flow_cur.copy_(self.fnet.flow)

@@ -136,10 +136,16 @@ class GeneratorPlan:
             self.trunk_flags = torch.zeros(B * ((h + 15) // 16) * ((w + 7) // 8), device=device, dtype=torch.int32)
             self.launches = 1 + 4 + 1
 
-    def run(self, lr_f32, lr_cpitch=3):
-        """x_in must already hold the packed input; lr_f32: fp32 tensor whose first 3 channels are LR RGB."""
+    def run_bicubic(self, lr_f32, lr_cpitch=3):
+        """bicubic_four(LR) for the output stage (lib/frvsr.py:84-86); independent of everything but the LR frame."""
+        call("teco_bicubic4_f32", ptr(lr_f32, f32), ptr(self.bic, f32), self.B, self.h, self.w, 3, lr_cpitch, stream_ptr())
+
+    def run(self, lr_f32, lr_cpitch=3, bicubic=True):
+        """x_in must already hold the packed input; lr_f32: fp32 tensor whose first 3 channels are LR RGB
+        (bicubic=False: the caller has already issued run_bicubic, e.g. on another stream)."""
         B, h, w = self.B, self.h, self.w
-        call("teco_bicubic4_f32", ptr(lr_f32, f32), ptr(self.bic, f32), B, h, w, 3, lr_cpitch, stream_ptr())
+        if bicubic:
+            self.run_bicubic(lr_f32, lr_cpitch)
         if self.fused:
             call("teco_trunk64_tc", B, h, w, 2 * self.nrb + 1, ptr(self.x_in, bf16), ptr(self.a, bf16), ptr(self.b, bf16),
                  ptr(self.trunk_w, bf16), ptr(self.trunk_b, f32), ptr(self.trunk_flags), stream_ptr())

@@ -140,6 +140,27 @@ if __name__ == "__main__":
         for _ in range(6):
             K.conv3x3_tc(x, wpk, torch.zeros(64, device="cuda"), y, cout=64, act=1)
         torch.cuda.synchronize()
+    if which == "pstamps":  # per-tile timeline of the persistent kernel (multi-wave layer), median over CTAs
+        from tecogan_b200 import _ffi
+        n, hh, cout = (int(os.environ.get("PS_N", 4)), int(os.environ.get("PS_H", 256)), int(os.environ.get("PS_COUT", 64)))
+        x = torch.randn(n, hh, hh, 64, device="cuda").to(torch.bfloat16)
+        wpk = K.packed_weight(torch.randn(3, 3, 64, cout, device="cuda") * 0.05, 64, cout)
+        y = torch.empty(n, hh, hh, cout, device="cuda", dtype=torch.bfloat16)
+        bz = torch.zeros(cout, device="cuda")
+        for _ in range(3):
+            K.conv3x3_tc(x, wpk, bz, y, cout=cout, act=1)
+        buf = torch.zeros(148 * 64, device="cuda", dtype=torch.int64)
+        _ffi.call("teco_debug_timing", _ffi.ptr(buf))
+        K.conv3x3_tc(x, wpk, bz, y, cout=cout, act=1)
+        torch.cuda.synchronize()
+        _ffi.call("teco_debug_timing", _ffi.ptr(None))
+        st = buf.view(148, 64).cpu().double()
+        t0 = st[:, 0:1]
+        tl = (st[:, 32:64] - t0).view(148, 8, 4)
+        print("tile: halo_seen(MMA start)  mma_issued  acc_seen(epi start)  epi_end   [median cycles since CTA start]")
+        for it in range(8):
+            print("  %d: " % it + "  ".join("%7.0f" % tl[:, it, k].median().item() for k in range(4)))
+        print("teardown median %.0f" % (st[:, 8] - st[:, 0]).median().item())
     if which == "stamps":  # phase timeline of one launch of the dominant layer (clock64 stamps per CTA)
         from tecogan_b200 import _ffi
         x = torch.randn(1, 128, 128, 64, device="cuda").to(torch.bfloat16)
