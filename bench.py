@@ -351,7 +351,7 @@ def main():
                        "num_resblock": NUM_RESBLOCK, "clips_per_gpu": 1, "frames_per_step": CLIP_FRAMES,
                        "l2": "flushed by a 256 MiB write between timed steps; inside a step the recurrence's own "
                              "working set is what it is (frames depend on each other)",
-                       "weights": "seeded random init (xavier, res-block/output weights x0.5)", "cuda_graph": True},
+                       "weights": "seeded random init (xavier, res-block/output weights x0.5)", "cuda_graph": True, "fnet_lookahead": LOOKAHEAD},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": CLIP_FRAMES * LR_H * LR_W * 3 * 4,
                     "d2h_bytes_per_step": CLIP_FRAMES * 16 * LR_H * LR_W * 3, "result": "uint8 HR frames (save_img quantisation)"},

@@ -1,5 +1,5 @@
 """Run-time configuration of the compute path (not part of the reference interface)."""
-_cfg = {"precision": "bf16", "train_precision": "fp32", "fused_trunk": False}
+_cfg = {"precision": "bf16", "train_precision": "fp32", "fused_trunk": __import__("os").environ.get("TECO_FUSED_TRUNK", "0") == "1"}
 
 
 def set_precision(p):

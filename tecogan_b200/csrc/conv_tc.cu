@@ -616,7 +616,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     };
     if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});   // (a single EW = 16 instantiation halves the SASS but
     else run(std::integral_constant<int, 16>{});                   //  measured 7.4 us vs 6.9 us on the 64->64 layer)
-    if (p.tma_out && threadIdx.x == 64) bulk_wait_all();           // all output tiles are written before the CTA retires
+    if (p.tma_out && threadIdx.x == 64) bulk_wait_read();          // smem outlives the last store's reads; visibility comes with grid completion
   }
 
   if (threadIdx.x == 64) STAMP(7);

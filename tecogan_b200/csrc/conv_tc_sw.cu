@@ -229,7 +229,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   const int x0 = tx * 8 * J, y0 = ty * TILE_ROWS;
   long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
 #define STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
-  if (threadIdx.x == 0) STAMP(0);
+#define GSTAMP(i) do { if (dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = (long long)t_; } } while (0)
+  if (threadIdx.x == 0) { STAMP(0); GSTAMP(26); }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.HST; ++i) {
@@ -257,9 +258,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   if (p.CS > 1) cluster_sync_all();   // every CTA's mbarriers are initialised before any multicast may signal them
   else __syncthreads();
   tcgen05_fence_after();
-  // Programmatic dependent launch is triggered LATE (when this CTA's MMAs have been issued, see the MMA warp): the next
-  // layer's CTAs then share the SM only with this layer's epilogue, run their prologue + weight fetch under it, and never
-  // pile up three layers deep (an early trigger let 2 CTAs of later layers land on the 20 idle SMs: 7.45 vs 6.5 us/layer).
+  // Programmatic dependent launch is triggered only once this CTA's own dependency wait has returned (producer warp):
+  // the previous layer has retired by then, so the next layer's CTAs share an SM with exactly one CTA of this layer, run
+  // their prologue + weight fetch under our halo load / MMAs / epilogue, and never pile up three layers deep (triggering
+  // in the prologue let 2 CTAs of later layers land on the 20 idle SMs: 7.45 vs 6.5 us/layer).
   if (!active || !p.late_trigger) pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) STAMP(1);
@@ -304,7 +306,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
     if (lane == 0) STAMP(9);
     pdl_wait();   // the previous kernel's output (our input x) is complete and visible from here on
-    if (lane == 0) STAMP(10);
+    if (p.late_trigger) pdl_launch_dependents();   // the layer before us has retired: at most two layers share an SM
+    if (lane == 0) { STAMP(10); GSTAMP(27); }
     if (active && p.tma_res) {   // the residual tile (same box as the output tile) lands long before the epilogue needs it
       if (lane == 0) mbar_expect_tx(smem_u32(res_full), (uint32_t)(J * 16384));
       __syncwarp();
@@ -351,7 +354,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     for (int b = 0; b < p.nblk; ++b) {
       mbar_wait_warp(smem_u32(&halo_full[hs]), hph);
       tcgen05_fence_after();
-      if (lane == 0 && b == 0) STAMP(2);
+      if (lane == 0 && b == 0) { STAMP(2); GSTAMP(28); }
       const uint32_t halo_addr = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
       for (int g = 0; g < slabs_per_blk; ++g) {
         mbar_wait_warp(smem_u32(&w_full[ws]), wph);
@@ -419,8 +422,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       if (++hs == p.HST) { hs = 0; hph ^= 1; }
     }
     if (elect_one()) tcgen05_commit(smem_u32(acc_full));
-    if (p.late_trigger) pdl_launch_dependents();
-    if (lane == 0) STAMP(5);
+    if (lane == 0) { STAMP(5); GSTAMP(29); }
     __syncwarp();
   } else if (warp >= 2 && active) {
     // ===================== epilogue (warps 2..5) =====================
@@ -561,12 +563,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       if (threadIdx.x == 64) {
         for (int j = 0; j < J; ++j) tma_store_4d(&tmap_y, smem_u32(stage_out + (size_t)j * 16384), n0, x0 + 8 * j, y0, n);
         bulk_commit();
-        bulk_wait_all();      // the writes are complete before this CTA (and with it the grid) can be considered finished
+        // shared memory must outlive the store's reads; global visibility to the next layer comes with grid completion
+        // (griddepcontrol.wait / stream order), as in any epilogue that ends with a TMA store
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
   }
 
-  if (threadIdx.x == 64) STAMP(7);
+  if (threadIdx.x == 64) { STAMP(7); GSTAMP(30); }
   tcgen05_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) STAMP(8);
@@ -615,6 +619,13 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   p.post_scale = d->post_scale; p.post_shift = d->post_shift;
   p.wpk = (const uint8_t*)wpk; p.bias = bias; p.res = (const __nv_bfloat16*)res; p.y = (__nv_bfloat16*)y;
   p.res_f32 = res_f32; p.out_f32 = out_f32; p.dbg = teco_g_dbg_timing;
+  if (p.dbg) {   // consecutive launches stamp consecutive [256][32] slices (tools/bench_conv.py chain)
+    static long long* last_base = nullptr;
+    static int launch_idx = 0;
+    if (last_base != teco_g_dbg_timing) { last_base = teco_g_dbg_timing; launch_idx = 0; }
+    p.dbg = teco_g_dbg_timing + (size_t)(launch_idx % 8) * 256 * 32;
+    ++launch_idx;
+  }
   p.nblk = d->Cin / CB;
   p.HST = p.nblk > 1 ? 2 : 1;
   static const int env_h1 = [] { const char* e = getenv("TECO_TC_H1"); return e ? atoi(e) : 1; }();

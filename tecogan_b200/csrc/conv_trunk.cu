@@ -11,9 +11,10 @@
 //   * TMEM, mbarriers and the bias table live across layers.
 // Layer schedule (buffers A, B are NHWC bf16 [N,H,W,64]):  l = 0: X -> A (ReLU);  odd l: A -> B (ReLU);
 // even l >= 2: B -> A with "+ A" (the residual).  Operand layouts / MMA issue / epilogue are those of conv_tc_sw.cu
-// (SWIZZLE_128B halo copies per kx, 3 K-split accumulator chains, 8 epilogue warps).
+// (one SWIZZLE_128B halo box with the horizontal taps as descriptor start offsets, 3 K-split accumulator chains,
+// 8 epilogue warps writing a swizzled staging tile that one TMA store sends out; the residual stays in registers).
 //
-// All CTAs must be co-resident (they wait on each other): grid <= SM count and ~205 KB smem => one CTA per SM; the
+// All CTAs must be co-resident (they wait on each other): grid <= SM count and ~175 KB smem => one CTA per SM; the
 // host refuses other shapes.
 #include <type_traits>
 #include "teco_common.cuh"
@@ -26,8 +27,9 @@ namespace {
 constexpr int TILE_ROWS = 16, HALO_ROWS = 18, CH = 64;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr uint32_t ROW_BYTES = 8 * 128;                          // one box row: 8 pixels x 128 B
-constexpr uint32_t COPY_BYTES = HALO_ROWS * ROW_BYTES;            // one kx-copy: 18 KB
+constexpr uint32_t ROW_BYTES = 10 * 128;                         // one halo row: 8 + 2 pixels x 128 B
+constexpr uint32_t HALO_BYTES = HALO_ROWS * ROW_BYTES;            // ONE 18x10 box; horizontal taps = 128-byte start offsets
+constexpr uint32_t HALO_REGION = (HALO_BYTES + 1023u) & ~1023u;   // 23 KB; doubles as the output staging tile (16 KB)
 constexpr uint32_t W_LAYER_BYTES = 9 * CH * 128;                  // 72 KB
 constexpr uint32_t SLAB_BYTES = 3 * CH * 128;                     // 3 taps
 constexpr int MAX_LAYERS = 48;
@@ -53,15 +55,23 @@ __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+// tm_x / tm_a / tm_b: halo boxes (64 ch, 10 px, 18 rows) for loads; tm_ao / tm_bo: output tiles (64 ch, 8 px, 16 rows) of A / B
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 trunk64_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_a,
-                  const __grid_constant__ CUtensorMap tm_b, const TrunkParams p) {
+                  const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_ao,
+                  const __grid_constant__ CUtensorMap tm_bo, const TrunkParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  uint8_t* halo = smem;                                  // 3 kx-copies
-  uint8_t* wbuf = smem + 3 * COPY_BYTES;                 // 2 layers of weights
+  uint8_t* halo = smem;                                  // one 18x10 halo box; output staging tile during the epilogue
+  uint8_t* wbuf = smem + HALO_REGION;                    // 2 layers of weights
   uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + 2 * W_LAYER_BYTES);
   uint64_t* halo_full = bars;        // [1]
   uint64_t* halo_empty = bars + 1;   // [1]
@@ -94,6 +104,8 @@ trunk64_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ao) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bo) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
@@ -138,13 +150,11 @@ trunk64_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       if (lane == 0) {
         mbar_wait(smem_u32(halo_empty), (uint32_t)((l & 1) ^ 1));
-        mbar_expect_tx(smem_u32(halo_full), 3 * COPY_BYTES);
+        mbar_expect_tx(smem_u32(halo_full), HALO_BYTES);
+        const CUtensorMap* tm = (l == 0) ? &tm_x : ((l & 1) ? &tm_a : &tm_b);
+        tma_load_4d(smem_u32(halo), tm, smem_u32(halo_full), 0, x0 - 1, y0 - 1, n);
       }
       __syncwarp();
-      if (lane < 3) {
-        const CUtensorMap* tm = (l == 0) ? &tm_x : ((l & 1) ? &tm_a : &tm_b);
-        tma_load_4d(smem_u32(halo + (size_t)lane * COPY_BYTES), tm, smem_u32(halo_full), 0, x0 - 1 + lane, y0 - 1, n);
-      }
       if (l + 2 < p.L) {    // weights of layer l+2 go into this layer's buffer once its MMAs have retired
         const int buf = l & 1;
         if (lane == 0) mbar_wait(smem_u32(&w_empty[buf]), (uint32_t)((l >> 1) & 1));
@@ -174,7 +184,7 @@ trunk64_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           for (int s = 0; s < CH / 16; ++s) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              const uint32_t a_off16 = ((uint32_t)kx * COPY_BYTES + (uint32_t)g * ROW_BYTES + (uint32_t)s * 32u) >> 4;
+              const uint32_t a_off16 = ((uint32_t)kx * 128u + (uint32_t)g * ROW_BYTES + (uint32_t)s * 32u) >> 4;
               const uint32_t b_off16 = ((uint32_t)(g * 3 + kx) * (CH * 128) + (uint32_t)s * 32u) >> 4;
               umma_bf16(tmem_base + (uint32_t)kx * CH, a_base + a_off16, b_base + b_off16, idesc, (g | s) ? 1u : 0u);
             }
@@ -193,13 +203,12 @@ trunk64_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;
     const int m = 32 * q + lane;
-    const int ry = m >> 3, rx = m & 7;
-    const int oy = y0 + ry, ox = x0 + rx;
-    const bool in_img = (oy < p.H) && (ox < p.W);
-    const size_t pix = ((size_t)n * p.H + oy) * p.W + ox;
     const int c0 = chalf * 32;
     const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
     unsigned int* my_flag = p.flags + blockIdx.x;
+    uint32_t resp[16];   // residual carried across layers (packed bf16 pairs)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) resp[i] = 0u;
     for (int l = 0; l < p.L; ++l) {
       mbar_wait_warp(smem_u32(acc_full), (uint32_t)(l & 1));
       tcgen05_fence_after();
@@ -213,47 +222,48 @@ trunk64_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty)) : "memory");
       const bool relu = (l == 0) || (l & 1);
       const bool has_res = (l >= 2) && !(l & 1);
-      __nv_bfloat16* out = (l & 1) ? p.b : p.a;
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float a = __uint_as_float(r[i]) + __uint_as_float(r2[i]) + __uint_as_float(r3[i]) + s_bias[l * CH + c0 + i];
         v[i] = relu ? fmaxf(a, 0.f) : a;
       }
-      if (in_img) {
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.a + pix * CH + c0);
+      if (has_res) {   // "+ A": this thread's own bf16 output of the last even layer, kept in registers
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint4 rr = rp[k];
-            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
-              v[8 * k + 2 * i] += f.x;
-              v[8 * k + 2 * i + 1] += f.y;
-            }
-          }
-        }
-        uint4* yp = reinterpret_cast<uint4*>(out + pix * CH + c0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t o[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
-            o[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          yp[k] = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 16; ++i) {
+          float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&resp[i]));
+          v[2 * i] += f.x;
+          v[2 * i + 1] += f.y;
         }
       }
-      // publish: CTA barrier (all epilogue stores happen-before thread 64), async-proxy fence for the neighbours' TMA
-      // reads, then the release store of the layer counter (cumulative at gpu scope)
+      uint32_t o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        o[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (!(l & 1)) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) resp[i] = o[i];
+      }
+      // staging tile = SWIZZLE_128B image of the output box: pixel m owns row m, its 64 B are chunks 4*chalf..+3 ^ (m & 7).
+      // The halo buffer is free: this layer's MMAs have completed (acc_full).
+      uint8_t* os = halo + (uint32_t)m * 128u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<uint4*>(os + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4)) =
+            make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if (threadIdx.x == 64) TSTAMP(l, 5);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
       if (threadIdx.x == 64) {
         TSTAMP(l, 6);
-        fence_proxy_async_global();   // (the release store below is the cumulative gpu-scope fence; no separate membar)
+        // one TMA store of the tile (clipped at the image border), complete before the layer counter is released:
+        // the neighbours' TMA halo reads and our own next halo load (which overwrites the staging tile) wait on it
+        tma_store_4d((l & 1) ? &tm_bo : &tm_ao, smem_u32(halo), 0, x0, y0, n);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        fence_proxy_async_global();
         st_release(my_flag, (unsigned int)(l + 1));
         TSTAMP(l, 7);
       }
@@ -283,10 +293,10 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int make_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int N, int H, int W) {
+int make_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int N, int H, int W, int box_w = 10, int box_h = HALO_ROWS) {
   const cuuint64_t gdim[4] = {(cuuint64_t)CH, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   const cuuint64_t gstr[3] = {(cuuint64_t)CH * 2, (cuuint64_t)W * CH * 2, (cuuint64_t)H * W * CH * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)CH, 8, (cuuint32_t)HALO_ROWS, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)CH, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -324,15 +334,17 @@ extern "C" int teco_trunk64_tc(int32_t N, int32_t H, int32_t W, int32_t num_laye
     teco_set_error("teco_trunk64_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return TECO_E_CUDA;
   }
-  CUtensorMap tx, ta, tb;
+  CUtensorMap tx, ta, tb, tao, tbo;
   int e1 = make_map(enc, &tx, x_in, N, H, W), e2 = make_map(enc, &ta, buf_a, N, H, W), e3 = make_map(enc, &tb, buf_b, N, H, W);
+  e2 |= make_map(enc, &tao, buf_a, N, H, W, 8, TILE_ROWS);
+  e3 |= make_map(enc, &tbo, buf_b, N, H, W, 8, TILE_ROWS);
   if (e1 || e2 || e3) {
     teco_set_error("teco_trunk64_tc: cuTensorMapEncodeTiled failed (%d %d %d)", e1, e2, e3);
     return TECO_E_CUDA;
   }
   cudaStream_t s = (cudaStream_t)stream;
   TECO_CUDA_CALL(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * (size_t)p.num_tiles, s));
-  const size_t smem_bytes = 1024 + 3 * COPY_BYTES + 2 * W_LAYER_BYTES + 16 * 8 + (size_t)num_layers * CH * sizeof(float);
+  const size_t smem_bytes = 1024 + HALO_REGION + 2 * W_LAYER_BYTES + 16 * 8 + (size_t)num_layers * CH * sizeof(float);
   static bool attr = false;
   if (!attr) {
     TECO_CUDA_CALL(cudaFuncSetAttribute(trunk64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
@@ -352,7 +364,7 @@ extern "C" int teco_trunk64_tc(int32_t N, int32_t H, int32_t W, int32_t num_laye
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, trunk64_tc_kernel, tx, ta, tb, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, trunk64_tc_kernel, tx, ta, tb, tao, tbo, p);
   if (le != cudaSuccess) {
     teco_set_error("teco_trunk64_tc: launch failed: %s", cudaGetErrorString(le));
     return TECO_E_CUDA;

@@ -140,6 +140,32 @@ if __name__ == "__main__":
         for _ in range(6):
             K.conv3x3_tc(x, wpk, torch.zeros(64, device="cuda"), y, cout=64, act=1)
         torch.cuda.synchronize()
+    if which == "chain":   # wall-clock (globaltimer) timeline of 8 consecutive trunk layers sharing SMs through PDL
+        from tecogan_b200 import _ffi
+        xin = torch.randn(1, 128, 128, 64, device="cuda").to(torch.bfloat16)
+        a, b = torch.zeros_like(xin), torch.zeros_like(xin)
+        ws = [K.packed_weight(torch.randn(3, 3, 64, 64, device="cuda") * 0.03, 64, 64) for _ in range(8)]
+        bz = torch.zeros(64, device="cuda")
+        def chain():
+            for i in range(0, 8, 2):
+                K.conv3x3_tc(a, ws[i], bz, b, cout=64, act=1)
+                K.conv3x3_tc(b, ws[i + 1], bz, a, cout=64, act=0, res=a)
+        chain(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        buf = torch.zeros(8 * 256 * 32, device="cuda", dtype=torch.int64)
+        _ffi.call("teco_debug_timing", _ffi.ptr(buf))
+        with torch.cuda.graph(g):
+            chain()
+        g.replay(); torch.cuda.synchronize()
+        buf.zero_()
+        g.replay(); torch.cuda.synchronize()
+        _ffi.call("teco_debug_timing", _ffi.ptr(None))
+        st = buf.view(8, 256, 32)[:, :128].cpu().double()
+        t0 = st[0, :, 26].min()
+        print("layer: cta_start  dep_wait_done  mma_start  mma_issued  epi_done   [ns since first CTA start; median (min..max) over 128 CTAs]")
+        for l in range(8):
+            print("  %d: " % l + "  ".join("%6.0f (%5.0f..%5.0f)" % ((st[l, :, k] - t0).median().item(), (st[l, :, k] - t0).min().item(),
+                                                                  (st[l, :, k] - t0).max().item()) for k in (26, 27, 28, 29, 30)))
     if which == "pstamps":  # per-tile timeline of the persistent kernel (multi-wave layer), median over CTAs
         from tecogan_b200 import _ffi
         n, hh, cout = (int(os.environ.get("PS_N", 4)), int(os.environ.get("PS_H", 256)), int(os.environ.get("PS_COUT", 64)))
