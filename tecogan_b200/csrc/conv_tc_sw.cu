@@ -52,6 +52,7 @@ struct TcParams {
   int nblk, WST, TPS, KS;              // Cin/64, weight ring stages, taps per weight slab (1 or 3), K-split chains
   int HST, CS, mcast, num_tiles;       // halo stages, cluster size, resident+multicast weights, real tile count
   int late_trigger;                    // trigger the dependent launch after the MMAs instead of after the prologue
+  uint32_t stage2_bytes;               // second staging region after the weights: residual tiles (conv) / ping-pong tile (tconv)
   int tma_out, tma_res;                // bf16 output / residual tiles travel through swizzled smem staging + TMA (Ncta == 64, conv)
   uint32_t copy_bytes, halo_stage_bytes, w_slab_bytes, tmem_cols;
   const uint8_t* wpk;
@@ -101,6 +102,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -207,7 +213,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   // stages, which are dead once the accumulators are complete
   uint8_t* stage_res = w_base + (size_t)p.WST * p.w_slab_bytes;
   uint8_t* stage_out = halo_base;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_res + (p.tma_res ? (size_t)J * 16384 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_res + p.stage2_bytes);
   uint64_t* halo_full = bars;
   uint64_t* halo_empty = bars + 2;
   uint64_t* w_full = bars + 4;
@@ -308,11 +314,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     pdl_wait();   // the previous kernel's output (our input x) is complete and visible from here on
     if (p.late_trigger) pdl_launch_dependents();   // the layer before us has retired: at most two layers share an SM
     if (lane == 0) { STAMP(10); GSTAMP(27); }
-    if (active && p.tma_res) {   // the residual tile (same box as the output tile) lands long before the epilogue needs it
-      if (lane == 0) mbar_expect_tx(smem_u32(res_full), (uint32_t)(J * 16384));
-      __syncwarp();
-      if (lane < J) tma_load_4d(smem_u32(stage_res + (size_t)lane * 16384), &tmap_r, smem_u32(res_full), n0, x0 + 8 * lane, y0, n);
-    }
     if (active) {
       int hs = 0;
       uint32_t hph = 0;
@@ -337,6 +338,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
         __syncwarp();
         if (++hs == p.HST) { hs = 0; hph ^= 1; }
+      }
+      if (p.tma_res) {   // the residual tile (same box as the output tile), after the halo: the MMAs are waiting for that one
+        if (lane == 0) mbar_expect_tx(smem_u32(res_full), (uint32_t)(J * 16384));
+        __syncwarp();
+        if (lane < J) tma_load_4d(smem_u32(stage_res + (size_t)lane * 16384), &tmap_r, smem_u32(res_full), n0, x0 + 8 * lane, y0, n);
       }
     } else if (p.mcast && lane == 0) {
       // padding CTA of a cluster: it only relays its share of the weights; stay until they have landed here too
@@ -512,6 +518,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
               }
               continue;
             }
+            if (MODE == 1 && EW == 32 && p.tma_out) {
+              // transposed conv: one staging tile per (sub-tile, output phase), two tiles in ping-pong (the dead halo stage and
+              // the region after the weights); the phase's 16x8 pixels go out through a 5-D map over the 2x interleaved output
+              const int t = j * 4 + ph;
+              uint8_t* stg = (t & 1) ? stage_res : stage_out;
+              if (t >= 2) {   // the store issued two steps ago has finished reading this tile
+                if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+              }
+              uint8_t* os = stg + (uint32_t)m * 128u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                  o[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(os + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+              fence_async_smem();
+              asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+              if (threadIdx.x == 64) {
+                tma_store_5d(&tmap_y, smem_u32(stg), n0, ph & 1, x0 + 8 * j, ph >> 1, n * p.H + y0);
+                bulk_commit();
+              }
+              continue;
+            }
             if (!in_img) continue;
             if (p.out_f32) {
               for (int i = 0; i < EW; ++i) {
@@ -556,6 +590,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     };
     if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});
     else run(std::integral_constant<int, 16>{});
+    if (MODE == 1 && p.tma_out && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (MODE == 0 && p.tma_out) {
       // generic-proxy smem writes -> visible to the async proxy, all epilogue warps done, then one thread stores the tiles
       fence_async_smem();
@@ -693,10 +728,12 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
   static const int env_tma = [] { const char* e = getenv("TECO_TC_TMA_EPI"); return e ? atoi(e) : 1; }();
-  p.tma_out = (env_tma && d->mode == 0 && y && !out_f32 && p.Ncta == 64) ? 1 : 0;
+  p.tma_out = (env_tma && y && !out_f32 && p.Ncta == 64 &&
+               (d->mode == 0 || (!res && p.nsplit == 1 && d->H % TILE_ROWS == 0))) ? 1 : 0;   // tconv: rows of (n, y) are one map dimension
   p.tma_res = (p.tma_out && res) ? 1 : 0;
+  p.stage2_bytes = p.tma_res ? (uint32_t)(J * 16384) : ((p.tma_out && d->mode == 1) ? 16384u : 0u);
   TECO_CHECK_ARG(!p.tma_out || (size_t)J * 16384 <= a_total, "teco_conv3x3_tc(one-tile): output staging does not fit the halo stages");
-  const size_t smem_bytes = a_total + (size_t)p.WST * p.w_slab_bytes + (p.tma_res ? (size_t)J * 16384 : 0) +
+  const size_t smem_bytes = a_total + (size_t)p.WST * p.w_slab_bytes + p.stage2_bytes +
                             (4 + 2 * MAX_WST + 2) * 8 + 256 * sizeof(float) + 16;
   static const int env_late = [] { const char* e = getenv("TECO_TC_LATE_TRIGGER"); return e ? atoi(e) : 1; }();
   p.late_trigger = (env_late && 2 * (smem_bytes + 1024) <= 228 * 1024) ? 1 : 0;   // only useful when two CTAs fit an SM
@@ -719,7 +756,20 @@ int teco_conv3x3_tc_one_tile(const teco_tc_desc* d, const void* x, const void* w
     return TECO_E_CUDA;
   }
   CUtensorMap tmap_y = tmap, tmap_r = tmap;   // placeholders when the staged epilogue is off
-  if (p.tma_out) {
+  if (p.tma_out && d->mode == 1) {
+    // output [N, 2H, 2W, C] as {C, px, x, py, n*H + y}: one box = the 16x8 pixels of one sub-pixel phase
+    const cuuint64_t odim[5] = {(cuuint64_t)d->Cout, 2, (cuuint64_t)d->W, 2, (cuuint64_t)d->N * d->H};
+    const cuuint64_t ostr[4] = {(cuuint64_t)d->Cout * 2, (cuuint64_t)d->Cout * 4, (cuuint64_t)d->W * d->Cout * 4,
+                                (cuuint64_t)d->W * d->Cout * 8};
+    const cuuint32_t obox[5] = {64, 1, 8, 1, (cuuint32_t)TILE_ROWS};
+    const cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+    cr = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, y, odim, ostr, obox, estr5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      teco_set_error("teco_conv3x3_tc(one-tile): cuTensorMapEncodeTiled (transposed-conv output) failed with CUresult %d", (int)cr);
+      return TECO_E_CUDA;
+    }
+  } else if (p.tma_out) {
     const cuuint64_t odim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     const cuuint64_t ostr[3] = {(cuuint64_t)d->Cout * 2, (cuuint64_t)d->W * d->Cout * 2, (cuuint64_t)d->H * d->W * d->Cout * 2};
     const cuuint32_t obox[4] = {64, 8, (cuuint32_t)TILE_ROWS, 1};
