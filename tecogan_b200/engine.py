@@ -57,6 +57,9 @@ class InferenceEngine:
             self.lr_next = torch.zeros_like(self.lr_in)
             self.flow_cur = torch.zeros_like(self.fnet.flow)
             self._side = torch.cuda.Stream(device=self.device)
+            # the generator chain is the critical path of a frame: its kernel nodes get the higher stream priority, the
+            # look-ahead fnet fills the SMs it leaves idle
+            self._crit = torch.cuda.Stream(device=self.device, priority=-1)
         else:
             self.pre_gen = torch.zeros((batch, 4 * h, 4 * w, 3), device=self.device, dtype=f32)
             self.pre_warp = torch.zeros_like(self.pre_gen)
@@ -227,7 +230,7 @@ class InferenceEngine:
             t.copy_(v)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=self._crit):
             body()
         for t, v in zip(state, snap):
             t.copy_(v)
