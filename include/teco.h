@@ -38,6 +38,10 @@ const char* teco_last_error(void);
 int teco_version(void);
 /* Fills props[0..7] = {sm_count, cc_major, cc_minor, max_smem_optin, l2_bytes, 0,0,0}. */
 int teco_device_props(int device, int64_t* props);
+/* Host utility: CRC32C (Castagnoli) of n bytes continuing from crc (0 to start); returns the CRC in [0, 2^32) or a negative
+   TECO_E_* code.  Used by tecogan_b200/tf_bundle.py to verify TensorFlow checkpoint blocks and tensors (the reference gets
+   this from tf.train.Saver, main.py:224,245,307). */
+int64_t teco_crc32c(const void* data, int64_t n, int64_t crc);
 
 /* ---------------------------------------------------------------------------------------
  * fp32 direct convolution (exact-parity path; also dgrad via flipped weights).

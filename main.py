@@ -3,8 +3,10 @@
 per-frame loop of main.py:253-268, `--mode train` follows main.py:273-430 (TecoGAN when --ratio > 0, else FRVSR).
 
 Differences forced by the environment, stated once:
-  * weights: TensorFlow checkpoints cannot be read here yet; --checkpoint takes a .pt file written by this
-    program (name -> tensor, TF variable names) or `random:<seed>` for a seeded xavier initialisation;
+  * weights: --checkpoint / --vgg_ckpt take TensorFlow checkpoints (V2 bundle prefix or V1 file), read WITHOUT TensorFlow by
+    tecogan_b200/tf_bundle.py (format restated from its public description; no real checkpoint was available to pin it),
+    a .pt file written by this program (name -> tensor, TF variable names), or `random:<seed>` for a seeded xavier
+    initialisation; training saves both a .pt file and a TF V2 bundle;
   * training data: when --input_video_dir is missing, seeded synthetic HR clips stand in for the TF queue loader
     (lib/dataloader.py:52-273, out of scope); the device half (Gaussian down-sampling, crops) is the real one;
   * --precision {bf16,fp32} selects tcgen05 tensor-core or fp32 CUDA-core convolutions for inference;
@@ -51,13 +53,71 @@ def parse_flags(argv=None):
     return ap.parse_args(argv)
 
 
-def load_checkpoint(store, spec, num_resblock, need_d=False, need_vgg=False):
+def load_checkpoint(store, spec, num_resblock, need_d=False, need_vgg=False, pre_trained_model=False, vgg_ckpt=None):
+    """--checkpoint: `random:<seed>`, a .pt file written by this main.py, or a TensorFlow checkpoint (V2 prefix such as
+    ./model/TecoGAN, or a V1 file) read without TensorFlow by tecogan_b200/tf_bundle.py.
+
+    TF checkpoints follow the reference: inference restores the generator + fnet variables and fails on a missing one
+    (Saver.restore, main.py:221-224,245); training with --pre_trained_model loads what exists, zero-fills missing
+    generator/fnet variables and leaves missing discriminator variables at their initial values (main.py:312-320,
+    lib/ops.py:370-391); without it everything must be present (main.py:346-349; Adam moments and beta powers are NOT
+    taken over -- they restart from zero, a documented deviation).  --vgg_ckpt is read the same way (main.py:322-343)."""
     import torch
-    from tecogan_b200.init_params import xavier_params
+    from tecogan_b200 import tf_bundle
+    from tecogan_b200.init_params import variable_shapes, xavier_params
     if spec.startswith('random:'):
         store.load(xavier_params(int(spec.split(':', 1)[1]), num_resblock, need_d, need_vgg))
+    elif tf_bundle.is_tf_checkpoint(spec):
+        reader = tf_bundle.load_checkpoint(spec)
+        shapes = variable_shapes(num_resblock, need_d, False)
+        gen_fnet = {k: v for k, v in shapes.items() if not k.startswith('tdiscriminator/')}
+        dis = {k: v for k, v in shapes.items() if k.startswith('tdiscriminator/')}
+        if pre_trained_model:
+            got = tf_bundle.get_existing_from_ckpt(reader, gen_fnet, rest_zero=True, print_level=1)
+            print('Prepare to load %d weights from the pre-trained model for generator and fnet' % len(got))
+            dgot = tf_bundle.get_existing_from_ckpt(reader, dis, print_level=0)
+            if dis:
+                print('Prepare to load %d weights from the pre-trained model for discriminator' % len(dgot))
+            got.update(dgot)
+        else:
+            missing = [k for k in shapes if not reader.has_tensor(k)]
+            if missing:
+                raise ValueError('checkpoint %s lacks %d variables of this graph, e.g. %s' % (spec, len(missing), missing[:3]))
+            got = tf_bundle.get_existing_from_ckpt(reader, shapes, print_level=0)
+        reader.close()
+        store.load({k: torch.from_numpy(v) for k, v in got.items()})
     else:
         store.load(torch.load(spec, map_location='cpu'))
+    if need_vgg and vgg_ckpt is not None:
+        load_vgg_checkpoint(store, vgg_ckpt)
+
+
+def load_vgg_checkpoint(store, vgg_ckpt):
+    """--vgg_ckpt (slim's vgg_19.ckpt, a V1 checkpoint): the 16 convolutions of vgg_19 (reference main.py:322-324,340-343)."""
+    import torch
+    from tecogan_b200 import tf_bundle
+    from tecogan_b200.init_params import variable_shapes
+    reader = tf_bundle.load_checkpoint(vgg_ckpt)
+    vshapes = {k: v for k, v in variable_shapes(1, False, True).items() if k.startswith('vgg_19/')}
+    missing = [k for k in vshapes if not reader.has_tensor(k)]
+    if missing:
+        raise ValueError('vgg checkpoint %s lacks %s' % (vgg_ckpt, missing[:3]))
+    store.load({k: torch.from_numpy(v) for k, v in tf_bundle.get_existing_from_ckpt(reader, vshapes, print_level=0).items()})
+    reader.close()
+    print('VGG19 restored successfully!!')
+
+
+def save_checkpoint(store, output_dir, step):
+    """Both a .pt file and a TensorFlow V2 bundle `model-<step>.{index,data-00000-of-00001}` (Saver.save naming,
+    main.py:362-366,418-421) holding every variable under its TF name plus `global_step`."""
+    import numpy as np
+    import torch
+    from tecogan_b200 import tf_bundle
+    params = {k: v.detach().cpu() for k, v in store.items()}
+    torch.save(params, os.path.join(output_dir, 'model-%d.pt' % step))
+    tensors = {k: v.numpy() for k, v in params.items()}
+    tensors['global_step'] = np.asarray(step, dtype=np.int64)
+    tf_bundle.write_bundle(os.path.join(output_dir, 'model-%d' % step), tensors)
 
 
 def inference(FLAGS):
@@ -131,9 +191,12 @@ def train(FLAGS):
     store = V.set_default_store(V.VariableStore(seed=FLAGS.rand_seed))   # same seed on every rank -> identical init
     gan = FLAGS.ratio > 0
     if FLAGS.checkpoint is not None:
-        load_checkpoint(store, FLAGS.checkpoint, FLAGS.num_resblock, gan, FLAGS.vgg_scaling > 0)
+        load_checkpoint(store, FLAGS.checkpoint, FLAGS.num_resblock, gan, FLAGS.vgg_scaling > 0,
+                        pre_trained_model=FLAGS.pre_trained_model, vgg_ckpt=FLAGS.vgg_ckpt)
+    elif FLAGS.vgg_scaling > 0 and FLAGS.vgg_ckpt is not None:
+        load_vgg_checkpoint(store, FLAGS.vgg_ckpt)
     elif FLAGS.vgg_scaling > 0:
-        print('[main] no vgg_19.ckpt reader yet: VGG19 uses seeded random weights (frozen)')
+        print('[main] --vgg_ckpt not given: VGG19 uses seeded random weights (frozen)')
     dev = torch.device('cuda', local_rank)
     lr0, tg0 = frvsr_gpu_data_loader(synthetic_hr_batch(FLAGS, 0, rank, dev), FLAGS)
     Net = TecoGAN(lr0, tg0, FLAGS) if gan else FRVSR(lr0, tg0, FLAGS)
@@ -158,15 +221,15 @@ def train(FLAGS):
                     print(name, value)
             if (run_step % FLAGS.save_freq) == 0 and rank == 0:
                 print('Save the checkpoint')
-                torch.save({k: v.detach().cpu() for k, v in store.items()}, os.path.join(FLAGS.output_dir, 'model-%d.pt' % run_step))
+                save_checkpoint(store, FLAGS.output_dir, run_step)
     except KeyboardInterrupt:
         if rank == 0:
             print('main.py: KeyboardInterrupt->saving the checkpoint')
-            torch.save({k: v.detach().cpu() for k, v in store.items()}, os.path.join(FLAGS.output_dir, 'model-%d.pt' % Net.global_step()))
+            save_checkpoint(store, FLAGS.output_dir, Net.global_step())
         print('main.py: quit')
         sys.exit(0)
     if rank == 0:
-        torch.save({k: v.detach().cpu() for k, v in store.items()}, os.path.join(FLAGS.output_dir, 'model-%d.pt' % Net.global_step()))
+        save_checkpoint(store, FLAGS.output_dir, Net.global_step())
     print('Optimization done!!!!!!!!!!!!')
     if world > 1:
         dist.destroy_process_group()

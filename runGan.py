@@ -47,7 +47,9 @@ elif runcase == 1:   # inference a trained model
     testpre = ['calendar']
     os.makedirs(dirstr, exist_ok=True)
     lr_root = "./LR/" if os.path.exists("./LR/") else "/root/reference/LR/"
-    ckpt = './model/TecoGAN.pt' if os.path.exists('./model/TecoGAN.pt') else 'random:1234'
+    # reference runGan.py:87: --checkpoint ./model/TecoGAN (a TF V2 bundle, read without TensorFlow); then our .pt; else seeded init
+    ckpt = ('./model/TecoGAN' if os.path.exists('./model/TecoGAN.index') else
+            './model/TecoGAN.pt' if os.path.exists('./model/TecoGAN.pt') else 'random:1234')
     for nn in range(len(testpre)):
         cmd1 = [sys.executable, MAIN, "--cudaID", "0", "--output_dir", dirstr, "--summary_dir", os.path.join(dirstr, 'log/'),
                 "--mode", "inference", "--input_dir_LR", os.path.join(lr_root, testpre[nn]), "--output_pre", testpre[nn],
@@ -65,6 +67,10 @@ elif runcase == 3:   # Train TecoGAN -- flags of record reference runGan.py:142-
             "--max_iter", "500000", "--save_freq", "10000", "--num_resblock", "16", "--vgg_scaling", "0.2",
             "--ratio", "0.01", "--Dt_mergeDs", "--Dt_ratio_max", "1.0", "--Dt_ratio_0", "1.0", "--Dt_ratio_add", "0.0",
             "--pingpang", "--pp_scaling", "0.5", "--D_LAYERLOSS"] + extra
+    if os.path.exists('./model/vgg_19.ckpt'):            # reference runGan.py:113-115,176
+        cmd1 += ["--vgg_ckpt", './model/vgg_19.ckpt']
+    if os.path.exists('./model/ourFRVSR.index'):         # reference runGan.py:121-133,201-207: start from the FRVSR weights
+        cmd1 += ["--pre_trained_model", "--checkpoint", './model/ourFRVSR']
     run_train(cmd1)
 elif runcase == 4:   # Train FRVSR -- flags of record reference runGan.py:250-286
     now_str = datetime.datetime.now().strftime("%m-%d-%H")
