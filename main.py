@@ -60,8 +60,8 @@ def load_checkpoint(store, spec, num_resblock, need_d=False, need_vgg=False, pre
     TF checkpoints follow the reference: inference restores the generator + fnet variables and fails on a missing one
     (Saver.restore, main.py:221-224,245); training with --pre_trained_model loads what exists, zero-fills missing
     generator/fnet variables and leaves missing discriminator variables at their initial values (main.py:312-320,
-    lib/ops.py:370-391); without it everything must be present (main.py:346-349; Adam moments and beta powers are NOT
-    taken over -- they restart from zero, a documented deviation).  --vgg_ckpt is read the same way (main.py:322-343)."""
+    lib/ops.py:370-391); without it everything must be present (main.py:346-349; optimiser state follows in
+    restore_train_state once the trainer exists).  --vgg_ckpt is read the same way (main.py:322-343)."""
     import torch
     from tecogan_b200 import tf_bundle
     from tecogan_b200.init_params import variable_shapes, xavier_params
@@ -87,7 +87,9 @@ def load_checkpoint(store, spec, num_resblock, need_d=False, need_vgg=False, pre
         reader.close()
         store.load({k: torch.from_numpy(v) for k, v in got.items()})
     else:
-        store.load(torch.load(spec, map_location='cpu'))
+        blob = torch.load(spec, map_location='cpu')      # variables only: optimiser slots / counters go through restore_train_state
+        store.load({k: v for k, v in blob.items() if not (k.endswith('/Adam') or k.endswith('/Adam_1') or k == 'global_step'
+                                                          or k.startswith('teco_b200/'))})
     if need_vgg and vgg_ckpt is not None:
         load_vgg_checkpoint(store, vgg_ckpt)
 
@@ -107,17 +109,49 @@ def load_vgg_checkpoint(store, vgg_ckpt):
     print('VGG19 restored successfully!!')
 
 
-def save_checkpoint(store, output_dir, step):
+def save_checkpoint(store, output_dir, step, train_state=None):
     """Both a .pt file and a TensorFlow V2 bundle `model-<step>.{index,data-00000-of-00001}` (Saver.save naming,
-    main.py:362-366,418-421) holding every variable under its TF name plus `global_step`."""
+    main.py:362-366,418-421) holding every variable under its TF name, `global_step`, and -- when the trainer is given --
+    the Adam moments under TF's slot names plus the step counters / EMAs needed for an exact resume."""
     import numpy as np
     import torch
     from tecogan_b200 import tf_bundle
     params = {k: v.detach().cpu() for k, v in store.items()}
+    params['global_step'] = torch.tensor(step, dtype=torch.int64)
+    if train_state is not None:
+        params.update(train_state.state_tensors())
     torch.save(params, os.path.join(output_dir, 'model-%d.pt' % step))
-    tensors = {k: v.numpy() for k, v in params.items()}
-    tensors['global_step'] = np.asarray(step, dtype=np.int64)
-    tf_bundle.write_bundle(os.path.join(output_dir, 'model-%d' % step), tensors)
+    tf_bundle.write_bundle(os.path.join(output_dir, 'model-%d' % step), {k: np.asarray(v.numpy()) for k, v in params.items()})
+
+
+def restore_train_state(train_state, spec):
+    """Continue a training run (reference main.py:346-349 "Loading everything from the checkpoint"): optimiser moments,
+    global_step and the EMAs from a checkpoint written by save_checkpoint, or -- for a TensorFlow checkpoint of the
+    reference -- the Adam slots it holds (found by name suffix) and global_step."""
+    import torch
+    from tecogan_b200 import tf_bundle
+    if spec.startswith('random:'):
+        return []
+    if tf_bundle.is_tf_checkpoint(spec):
+        reader = tf_bundle.load_checkpoint(spec)
+        keys = reader.keys()
+
+        def get(name):
+            if reader.has_tensor(name):
+                return reader.get_tensor(name)
+            if name.endswith('/Adam') or name.endswith('/Adam_1'):
+                hits = [k for k in keys if k.endswith('/' + name)]
+                if len(hits) == 1:
+                    return reader.get_tensor(hits[0])
+            return None
+        missing = train_state.load_state(get)
+        reader.close()
+    else:
+        blob = torch.load(spec, map_location='cpu')
+        missing = train_state.load_state(lambda name: blob.get(name))
+    if missing:
+        print('[main] resume: %d state entries not in the checkpoint (kept at their initial values), e.g. %s' % (len(missing), missing[:3]))
+    return missing
 
 
 def inference(FLAGS):
@@ -201,6 +235,9 @@ def train(FLAGS):
     lr0, tg0 = frvsr_gpu_data_loader(synthetic_hr_batch(FLAGS, 0, rank, dev), FLAGS)
     Net = TecoGAN(lr0, tg0, FLAGS) if gan else FRVSR(lr0, tg0, FLAGS)
     print('Finish building the network.')
+    if FLAGS.checkpoint is not None and not FLAGS.pre_trained_model:
+        print('Loading everything from the checkpoint to continue the training...')
+        restore_train_state(Net.train, FLAGS.checkpoint)
     frame_len = (FLAGS.RNN_N * 2 - 1) if FLAGS.pingpang else FLAGS.RNN_N
     max_iter, start = FLAGS.max_iter, time.time()
     try:
@@ -221,15 +258,15 @@ def train(FLAGS):
                     print(name, value)
             if (run_step % FLAGS.save_freq) == 0 and rank == 0:
                 print('Save the checkpoint')
-                save_checkpoint(store, FLAGS.output_dir, run_step)
+                save_checkpoint(store, FLAGS.output_dir, run_step, Net.train)
     except KeyboardInterrupt:
         if rank == 0:
             print('main.py: KeyboardInterrupt->saving the checkpoint')
-            save_checkpoint(store, FLAGS.output_dir, Net.global_step())
+            save_checkpoint(store, FLAGS.output_dir, Net.global_step(), Net.train)
         print('main.py: quit')
         sys.exit(0)
     if rank == 0:
-        save_checkpoint(store, FLAGS.output_dir, Net.global_step())
+        save_checkpoint(store, FLAGS.output_dir, Net.global_step(), Net.train)
     print('Optimization done!!!!!!!!!!!!')
     if world > 1:
         dist.destroy_process_group()

@@ -413,6 +413,65 @@ class _TrainState:
                      "gen_outputs": self._gen_outputs, "t_balance": scal_host[0], "tb_ema": self.tb_ema}
         return self.last
 
+    # ---- checkpoint / resume (reference: tf.train.Saver over GLOBAL_VARIABLES, main.py:307,346-349) -------------------
+    def state_tensors(self):
+        """Everything besides the model variables that a resumed run needs, as {name: CPU tensor}.  Adam moments use
+        TensorFlow's slot names (`<variable>/Adam` = m, `<variable>/Adam_1` = v), `global_step` is the Saver's; the rest
+        (per-optimiser step counts, which TF keeps as beta powers, and the EMAs of lib/Teco.py:415-423,455-461) lives
+        under `teco_b200/`."""
+        out = {"global_step": torch.tensor(self.global_step, dtype=torch.int64)}
+        for tag, opt in (("g", self.opt_g), ("f", self.opt_f), ("d", self.opt_d)):
+            if opt is None:
+                continue
+            for k, (o, n) in opt.views.items():
+                shape = self.store[k].shape
+                out[k + "/Adam"] = opt.m[o:o + n].view(shape).detach().cpu().clone()
+                out[k + "/Adam_1"] = opt.v[o:o + n].view(shape).detach().cpu().clone()
+            out["teco_b200/adam_steps_" + tag] = torch.tensor(opt.t, dtype=torch.int64)
+        out["teco_b200/tb_ema"] = torch.tensor(self.tb_ema, dtype=torch.float64)
+        out["teco_b200/loss_ema"] = torch.tensor(self.loss_ema or [], dtype=torch.float64)
+        out["teco_b200/d_counters"] = torch.tensor([self.counter1, self.counter2], dtype=torch.int64)
+        return out
+
+    def load_state(self, get):
+        """Inverse of state_tensors.  `get(name)` returns an array-like or None; Adam slots are also looked up by the
+        suffix TensorFlow may have produced (`<optimizer scope>/<variable>/Adam`).  Missing pieces keep their fresh
+        values (moments 0, counters 0) and are reported in the returned list."""
+        missing = []
+
+        def fetch(name):
+            v = get(name)
+            if v is None:
+                missing.append(name)
+                return None
+            return torch.as_tensor(v)
+        gs = fetch("global_step")
+        if gs is not None:
+            self.global_step = int(gs)
+        for tag, opt in (("g", self.opt_g), ("f", self.opt_f), ("d", self.opt_d)):
+            if opt is None:
+                continue
+            for k, (o, n) in opt.views.items():
+                for slot, buf in (("/Adam", opt.m), ("/Adam_1", opt.v)):
+                    v = fetch(k + slot)
+                    if v is not None:
+                        if v.numel() != n:
+                            raise ValueError('Wrong shape in for {} in ckpt,expected {}, got {}.'.format(
+                                k + slot, str(tuple(self.store[k].shape)), str(tuple(v.shape))))
+                        buf[o:o + n].copy_(v.reshape(-1).to(dtype=torch.float32))
+            t = fetch("teco_b200/adam_steps_" + tag)
+            opt.t = int(t) if t is not None else self.global_step     # TF checkpoints: every optimiser stepped each iteration
+        v = fetch("teco_b200/tb_ema")
+        if v is not None:
+            self.tb_ema = float(v)
+        v = fetch("teco_b200/loss_ema")
+        if v is not None and v.numel():
+            self.loss_ema = [float(x) for x in v.reshape(-1)]
+        v = fetch("teco_b200/d_counters")
+        if v is not None:
+            self.counter1, self.counter2 = int(v[0]), int(v[1])
+        return missing
+
     def update_list_avg(self):
         avg = list(self.loss_ema or [])
         if self.GAN:

@@ -192,3 +192,39 @@ def test_bf16_tensor_core_tecogan_step_with_vgg_close_to_fp32_oracle():
     want = np.array([float(v) for v in ref["update_list"]])
     np.testing.assert_allclose(np.array(out["update_list"]), want, rtol=4e-2, atol=2e-3)
     assert out["with_d"] == ref["with_d"]
+
+
+@pytest.mark.parametrize("fmt", ["tf", "pt"])
+def test_checkpoint_resume_continues_bit_exactly(tmp_path, fmt):
+    """Saver semantics (reference main.py:307,346-349,418-421): save after two steps, restore weights + Adam moments +
+    step counters + EMAs into a fresh process state, and the third step equals the uninterrupted run bit for bit --
+    through the TensorFlow V2 bundle written by tecogan_b200/tf_bundle.py as well as through the .pt file."""
+    import main as M
+    from tecogan_b200.lib.Teco import TecoGAN
+    g, FL, P = _case("teco_nopp")
+    ri, rt = torch.from_numpy(g["r_inputs"]).cuda(), torch.from_numpy(g["r_targets"]).cuda()
+    st = _fresh_store(P)
+    net = TecoGAN(ri, rt, FL)
+    net.train()
+    net.train()
+    M.save_checkpoint(st, str(tmp_path), net.global_step(), net.train)
+    net.train()
+    want = {k: v.detach().cpu().clone() for k, v in st.items()}
+    want_ema, want_tb = list(net.train.loss_ema), net.train.tb_ema
+
+    from tecogan_b200 import variables as V
+    st2 = V.set_default_store(V.VariableStore())
+    spec = str(tmp_path / "model-2") + ("" if fmt == "tf" else ".pt")
+    M.load_checkpoint(st2, spec, FL.num_resblock, need_d=True, need_vgg=FL.vgg_scaling > 0)
+    if FL.vgg_scaling > 0:            # the frozen VGG weights are part of neither scope list of the reference's restore
+        st2.load({k: v for k, v in P.items() if k.startswith("vgg_19/")})
+    net2 = TecoGAN(ri, rt, FL)
+    missing = M.restore_train_state(net2.train, spec)
+    assert missing == [] and net2.global_step() == 2 and net2.train.opt_g.t == 2
+    net2.train()
+    assert net2.global_step() == 3
+    for k in want:
+        if k in st2:
+            assert torch.equal(st2[k].detach().cpu(), want[k]), k
+    assert net2.train.tb_ema == want_tb
+    np.testing.assert_array_equal(np.array(net2.train.loss_ema), np.array(want_ema))
