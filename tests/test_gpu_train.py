@@ -195,9 +195,10 @@ def test_bf16_tensor_core_tecogan_step_with_vgg_close_to_fp32_oracle():
 
 
 @pytest.mark.parametrize("fmt", ["tf", "pt"])
-def test_checkpoint_resume_continues_bit_exactly(tmp_path, fmt):
+def test_checkpoint_resume_restores_everything(tmp_path, fmt):
     """Saver semantics (reference main.py:307,346-349,418-421): save after two steps, restore weights + Adam moments +
-    step counters + EMAs into a fresh process state, and the third step equals the uninterrupted run bit for bit --
+    step counters + EMAs into a fresh process state -- bit-exact state -- and the third step lands where the uninterrupted
+    run does (the weight-gradient kernels accumulate with atomics, so two runs of one step agree to rounding, not bits),
     through the TensorFlow V2 bundle written by tecogan_b200/tf_bundle.py as well as through the .pt file."""
     import main as M
     from tecogan_b200.lib.Teco import TecoGAN
@@ -208,6 +209,8 @@ def test_checkpoint_resume_continues_bit_exactly(tmp_path, fmt):
     net.train()
     net.train()
     M.save_checkpoint(st, str(tmp_path), net.global_step(), net.train)
+    saved_state = net.train.state_tensors()
+    saved_w = {k: v.detach().cpu().clone() for k, v in st.items()}
     net.train()
     want = {k: v.detach().cpu().clone() for k, v in st.items()}
     want_ema, want_tb = list(net.train.loss_ema), net.train.tb_ema
@@ -221,10 +224,20 @@ def test_checkpoint_resume_continues_bit_exactly(tmp_path, fmt):
     net2 = TecoGAN(ri, rt, FL)
     missing = M.restore_train_state(net2.train, spec)
     assert missing == [] and net2.global_step() == 2 and net2.train.opt_g.t == 2
+    restored = net2.train.state_tensors()
+    assert set(restored) == set(saved_state)
+    for k, v in saved_state.items():                       # moments, counters, EMAs: exactly what was saved
+        assert torch.equal(restored[k], v), k
+    for k, v in saved_w.items():
+        if k in st2:
+            assert torch.equal(st2[k].detach().cpu(), v), k
     net2.train()
     assert net2.global_step() == 3
+    lr = FL.learning_rate
     for k in want:
-        if k in st2:
-            assert torch.equal(st2[k].detach().cpu(), want[k]), k
-    assert net2.train.tb_ema == want_tb
-    np.testing.assert_array_equal(np.array(net2.train.loss_ema), np.array(want_ema))
+        if k in st2 and not k.startswith("vgg_19/"):
+            d = (st2[k].detach().cpu() - want[k]).abs()
+            # a lost moment would move most elements by ~lr; agreement is to a small fraction of one Adam step
+            assert d.max().item() < 0.5 * lr and (d < 0.02 * lr).float().mean().item() > 0.99, (k, d.max().item())
+    assert abs(net2.train.tb_ema - want_tb) < 1e-6
+    np.testing.assert_allclose(np.array(net2.train.loss_ema), np.array(want_ema), rtol=1e-4, atol=1e-7)
