@@ -117,8 +117,10 @@ def cpu_reference_fps(max_frames, threads, budget_s=12.0):
     from oracle import teco_oracle as O
     torch.set_num_threads(threads)
     clip = synthetic_clip(max_frames, LR_H, LR_W, seed=0)
-    pg = O.damp_generator(O.init_generator(seed=1234, num_resblock=NUM_RESBLOCK))
-    pf = O.init_fnet(seed=4321)
+    from tecogan_b200.init_params import xavier_params
+    pw = xavier_params(1234, NUM_RESBLOCK)          # the same seeded weights the CUDA arm runs (TF variable names)
+    pg = {k: v for k, v in pw.items() if k.startswith("generator/")}
+    pf = {k: v for k, v in pw.items() if k.startswith("fnet/")}
     h, w = LR_H, LR_W
     with torch.no_grad():
         O.inference_sequence(pg, pf, [clip[0], clip[1]], NUM_RESBLOCK)   # warm the thread pool / allocator
@@ -190,7 +192,7 @@ def main():
     from tecogan_b200 import _ffi, config, variables as V
     from tecogan_b200 import kernels as K
     from tecogan_b200.engine import InferenceEngine
-    from oracle import teco_oracle as O   # weights only: seeded init shared with the CPU baseline leg
+    from tecogan_b200.init_params import xavier_params   # product-side seeded init; oracle/ is only the cpu_baseline leg
 
     # count our C-ABI kernel launches
     counter = {"n": 0}
@@ -206,7 +208,7 @@ def main():
 
     config.set_precision("bf16")
     st = V.set_default_store(V.VariableStore())
-    st.load({**O.damp_generator(O.init_generator(seed=1234, num_resblock=NUM_RESBLOCK)), **O.init_fnet(seed=4321)})
+    st.load(xavier_params(1234, NUM_RESBLOCK))
     eng = InferenceEngine(LR_H, LR_W, NUM_RESBLOCK, batch=1, use_graph=True)
 
     clip_host = synthetic_clip(CLIP_FRAMES, LR_H, LR_W, seed=rank).pin_memory()

@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import teco_oracle as O                      # weights only (test/bench infrastructure)
+from tecogan_b200.init_params import xavier_params  # noqa: E402
 from tecogan_b200 import config, variables as V
 from tecogan_b200.engine import InferenceEngine
 
@@ -15,7 +15,7 @@ w = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 config.set_precision("bf16")
 st = V.set_default_store(V.VariableStore())
-st.load({**O.damp_generator(O.init_generator(seed=1234, num_resblock=16)), **O.init_fnet(seed=4321)})
+st.load(xavier_params(1234, 16))
 clip = torch.rand(T, h, w, 3, device="cuda")
 outs = {}
 for la in (False, True):
