@@ -7,8 +7,10 @@ Differences forced by the environment, stated once:
     tecogan_b200/tf_bundle.py (format restated from its public description; no real checkpoint was available to pin it),
     a .pt file written by this program (name -> tensor, TF variable names), or `random:<seed>` for a seeded xavier
     initialisation; training saves both a .pt file and a TF V2 bundle;
-  * training data: when --input_video_dir is missing, seeded synthetic HR clips stand in for the TF queue loader
-    (lib/dataloader.py:52-273, out of scope); the device half (Gaussian down-sampling, crops) is the real one;
+  * training data: --input_video_dir is read by a thread-pool loader with the reference's directory layout and
+    augmentations (tecogan_b200/lib/dataloader.py::HRClipLoader, after lib/dataloader.py:147-273) instead of TF queue
+    runners; when the flag is empty, seeded synthetic HR clips stand in; the device half (Gaussian down-sampling, crops)
+    is the same either way;
   * --precision {bf16,fp32} selects tcgen05 tensor-core or fp32 CUDA-core convolutions for inference;
   * under `torchrun` each rank trains on its own clip shard with one NCCL all-reduce per step.
 """
@@ -232,7 +234,20 @@ def train(FLAGS):
     elif FLAGS.vgg_scaling > 0:
         print('[main] --vgg_ckpt not given: VGG19 uses seeded random weights (frozen)')
     dev = torch.device('cuda', local_rank)
-    lr0, tg0 = frvsr_gpu_data_loader(synthetic_hr_batch(FLAGS, 0, rank, dev), FLAGS)
+    if FLAGS.input_video_dir:
+        # HR clips from disk (reference lib/dataloader.py:147-273): decoded + augmented on queue_thread host threads,
+        # uploaded from pinned memory; LR synthesis and target crops happen on the device (frvsr_gpu_data_loader)
+        from tecogan_b200.lib.dataloader import HRClipLoader
+        loader = HRClipLoader(FLAGS, rank=rank, world=world)
+        clip_iter = loader.batches()
+        next_hr = lambda step: next(clip_iter).to(dev, non_blocking=True)
+        if FLAGS.max_iter is None:            # reference main.py:370-375
+            if FLAGS.max_epoch is None:
+                raise ValueError('one of max_epoch or max_iter should be provided')
+            FLAGS.max_iter = FLAGS.max_epoch * loader.steps_per_epoch
+    else:
+        next_hr = lambda step: synthetic_hr_batch(FLAGS, step, rank, dev)
+    lr0, tg0 = frvsr_gpu_data_loader(next_hr(0), FLAGS)
     Net = TecoGAN(lr0, tg0, FLAGS) if gan else FRVSR(lr0, tg0, FLAGS)
     print('Finish building the network.')
     if FLAGS.checkpoint is not None and not FLAGS.pre_trained_model:
@@ -242,7 +257,7 @@ def train(FLAGS):
     max_iter, start = FLAGS.max_iter, time.time()
     try:
         for step in range(max_iter):
-            lr_, tg_ = frvsr_gpu_data_loader(synthetic_hr_batch(FLAGS, step, rank, dev), FLAGS)
+            lr_, tg_ = frvsr_gpu_data_loader(next_hr(step), FLAGS)
             res = Net.train(lr_, tg_)
             run_step = Net.global_step()
             if step == 0 and rank == 0:
