@@ -4,10 +4,12 @@ hot path, so that the reference's own Python (lib/ops.py, lib/frvsr.py, lib/Teco
 
 Scope and honesty: TensorFlow itself is not installable here, so the *primitive* semantics
 (SAME padding, conv2d_transpose alignment, legacy resize, dense_image_warp, fused BN) come
-from oracle/teco_oracle.py -- the goldens therefore pin the reference's WIRING (layer order,
-scopes/variable names, activations, channel orders, loss formulas, slicing) and NOT those
-[TF-ext] primitives.  Used only by tests/golden/make_golden.py (never at test time on the
-GPU box, never by the product).
+from tests/golden/tf_ext_ref.py -- numpy written from the operators' published definitions,
+sharing no code with oracle/teco_oracle.py.  The goldens therefore pin the reference's WIRING
+(layer order, scopes/variable names, activations, channel orders, loss formulas, slicing) by the
+reference's own code, and the [TF-ext] primitives by a derivation that is independent of the
+oracle under test (they are still a restatement of TensorFlow, not TensorFlow).  Used only by
+tests/golden/make_golden.py (never at test time on the GPU box, never by the product).
 
 Tensors are float32 numpy arrays (subclass with get_shape/set_shape) because the reference
 uses negative-step slicing, which torch tensors reject.
@@ -19,7 +21,7 @@ import types
 import numpy as np
 import torch
 
-from oracle import teco_oracle as O
+from tests.golden import tf_ext_ref as X
 
 
 class _Shape(tuple):
@@ -135,7 +137,7 @@ def slim_conv2d(inputs, num_outputs, kernel_size, stride=1, padding='SAME', data
         w = _var('weights')
         assert tuple(w.shape) == (k[0], k[1], inputs.shape[-1], num_outputs), (sc.name, w.shape)
         b = _var('biases') if biases_initializer is not None else None
-        y = _a(O.conv2d(_t(inputs), w, b, stride))
+        y = A(X.conv2d(inputs, w.numpy(), None if b is None else b.numpy(), stride, 'SAME'))
         if activation_fn is not None:
             y = activation_fn(y)
         _collect(outputs_collections, sc.name, y)
@@ -150,19 +152,19 @@ def slim_conv2d_transpose(inputs, num_outputs, kernel_size, stride=1, padding='S
         w = _var('weights')
         assert tuple(w.shape) == (k[0], k[1], num_outputs, inputs.shape[-1]), (sc.name, w.shape)
         b = _var('biases') if biases_initializer is not None else None
-        return _a(O.conv2d_transpose(_t(inputs), w, b, stride))
+        return A(X.conv2d_transpose(inputs, w.numpy(), None if b is None else b.numpy(), stride))
 
 
 def slim_batch_norm(inputs, decay=0.999, epsilon=0.001, updates_collections=None, scale=False, fused=None,
                     is_training=True, scope=None):
     assert is_training and not scale
     with variable_scope(scope, 'BatchNorm'):
-        return _a(O.batchnorm_train(_t(inputs), _var('beta'), epsilon))
+        return A(X.batch_norm_train(inputs, _var('beta').numpy(), epsilon))
 
 
 def slim_max_pool2d(inputs, kernel_size, stride=2, padding='VALID', scope=None, outputs_collections=None):
     assert list(kernel_size) == [2, 2] and stride == 2 and padding == 'VALID'
-    return _a(O.maxpool(_t(inputs)))
+    return A(X.max_pool_2x2(inputs))
 
 
 def slim_repeat(inputs, repetitions, layer, *args, **kwargs):
@@ -196,7 +198,7 @@ class LeakyReLU:
         self.alpha = alpha
 
     def call(self, x):
-        return _a(O.lrelu(_t(x), self.alpha))
+        return A(X.leaky_relu(x, self.alpha))
 
 
 def tf_shape(x):
@@ -220,11 +222,11 @@ def tf_stack(vals, axis=0):
 
 
 def resize_images(x, size):
-    return _a(O.resize_bilinear_legacy(_t(x), int(size[0]), int(size[1])))
+    return A(X.resize_bilinear(x, int(size[0]), int(size[1])))
 
 
 def dense_image_warp(image, flow):
-    return _a(O.dense_image_warp(_t(image), _t(flow)))
+    return A(X.dense_image_warp(image, flow))
 
 
 def crop_to_bounding_box(x, oy, ox, th, tw):
@@ -248,8 +250,7 @@ def reduce_sum(x, axis=None, keepdims=False):
 
 def nn_conv2d(x, filt, strides, padding, name=None):
     assert padding == "VALID"
-    y = torch.nn.functional.conv2d(_t(x).permute(0, 3, 1, 2), _t(filt).permute(3, 2, 0, 1), stride=strides[1])
-    return _a(y.permute(0, 2, 3, 1).contiguous())
+    return A(X.conv2d(x, np.asarray(filt), None, strides[1], "VALID"))
 
 
 class _Optimizer:
@@ -307,7 +308,7 @@ def install():
     tf.reduce_mean = reduce_mean
     tf.reduce_sum = reduce_sum
     tf.pad = tf_pad
-    tf.space_to_depth = lambda x, bs: _a(O.space_to_depth4(_t(x)))
+    tf.space_to_depth = lambda x, bs: A(X.space_to_depth(x, bs))
     tf.assign = lambda ref, val: val
     tf.assign_add = lambda ref, val: ref + val
     tf.group = lambda *a: None
@@ -317,7 +318,7 @@ def install():
     tf.zeros_initializer = lambda: None
     tf.GraphKeys = types.SimpleNamespace(MODEL_VARIABLES="mv", TRAINABLE_VARIABLES="tv", GLOBAL_VARIABLES="gv",
                                          UPDATE_OPS="uo", SUMMARIES="s")
-    tf.nn = types.SimpleNamespace(relu=relu, sigmoid=lambda x: _a(torch.sigmoid(_t(x))), conv2d=nn_conv2d)
+    tf.nn = types.SimpleNamespace(relu=relu, sigmoid=lambda x: A(X.sigmoid(x)), conv2d=nn_conv2d)
     tf.image = types.SimpleNamespace(resize_images=resize_images, crop_to_bounding_box=crop_to_bounding_box)
     tf.layers = types.SimpleNamespace(Dense=Dense)
     tf.train = types.SimpleNamespace(

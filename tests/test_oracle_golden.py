@@ -136,3 +136,62 @@ def test_tf_adam_matches_closed_form_first_step():
     opt.apply(p, {"a": torch.tensor([0.5, -0.25])})
     # step 1: m=(1-b1)g, v=(1-b2)g^2, lr_t = lr*sqrt(1-b2)/(1-b1) => delta = lr*g/(|g| + eps*sqrt(1-b2)) ~ lr*sign(g)
     assert torch.allclose(p["a"], torch.tensor([0.9, -1.9]), atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# [TF-ext] primitives: the oracle's torch restatement against tests/golden/tf_ext_ref.py, a numpy derivation from the
+# operators' published definitions that shares no code with the oracle (the goldens above are generated on top of
+# tf_ext_ref, so neither check is circular).  Ragged sizes, both strides, clamp cases.
+from tests.golden import tf_ext_ref as X  # noqa: E402
+
+
+def _rnd(seed, *shape, lo=-1.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+
+def test_tfext_conv2d_same_padding_all_strides():
+    for seed, (n, h, w, ci, co, k, s) in enumerate([(2, 7, 9, 5, 4, 3, 1), (1, 8, 8, 3, 6, 3, 2), (2, 9, 7, 4, 3, 4, 2),
+                                                    (1, 16, 12, 3, 5, 4, 2), (1, 5, 5, 6, 2, 1, 1), (1, 13, 11, 2, 3, 3, 2)]):
+        x, wt, b = _rnd(seed, n, h, w, ci), _rnd(100 + seed, k, k, ci, co), _rnd(200 + seed, co)
+        np.testing.assert_allclose(O.conv2d(x, wt, b, s).numpy(), X.conv2d(x.numpy(), wt.numpy(), b.numpy(), s), rtol=1e-5, atol=1e-5)
+
+
+def test_tfext_conv2d_transpose_is_the_gradient_of_the_same_conv():
+    for seed, (n, h, w, ci, co) in enumerate([(1, 4, 5, 3, 2), (2, 7, 3, 4, 5), (1, 1, 1, 2, 2), (1, 6, 6, 8, 8)]):
+        x, wt, b = _rnd(seed, n, h, w, ci), _rnd(10 + seed, 3, 3, co, ci), _rnd(20 + seed, co)
+        ref = X.conv2d_transpose(x.numpy(), wt.numpy(), b.numpy(), 2)
+        assert ref.shape == (n, 2 * h, 2 * w, co)
+        np.testing.assert_allclose(O.conv2d_transpose(x, wt, b, 2).numpy(), ref, rtol=1e-5, atol=1e-5)
+        # and the definition itself: <conv_T(x), y> == <x, conv_same_s2(y)> with the same filter read as HWIO [kh,kw,Cout->Cin]
+        y = _rnd(30 + seed, n, 2 * h, 2 * w, co)
+        lhs = float((X.conv2d_transpose(x.numpy(), wt.numpy(), None, 2).astype(np.float64) * y.numpy()).sum())
+        rhs = float((x.numpy().astype(np.float64) * X.conv2d(y.numpy(), wt.numpy(), None, 2)).sum())
+        assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_tfext_dense_image_warp_axis_order_and_clamp():
+    img = _rnd(1, 2, 9, 11, 3)
+    # in-range fractional flow, large out-of-range flow (both signs: exercises floor clamp to [0,size-2] and alpha clamp to [0,1])
+    for seed, scale in ((2, 1.7), (3, 30.0)):
+        flow = _rnd(seed, 2, 9, 11, 2) * scale
+        np.testing.assert_allclose(O.dense_image_warp(img, flow).numpy(), X.dense_image_warp(img.numpy(), flow.numpy()),
+                                   rtol=1e-5, atol=1e-5)
+    # channel 0 of the flow is the ROW displacement: shifting by (+1, 0) reads the pixel one row above
+    flow = torch.zeros(2, 9, 11, 2)
+    flow[..., 0] = 1.0
+    out = X.dense_image_warp(img.numpy(), flow.numpy())
+    np.testing.assert_allclose(out[:, 1:], img.numpy()[:, :-1], atol=1e-6)
+    np.testing.assert_allclose(O.dense_image_warp(img, flow).numpy(), out, atol=1e-6)
+
+
+def test_tfext_legacy_resize_batchnorm_pool_s2d():
+    x = _rnd(5, 2, 6, 10, 4)
+    for oh, ow in ((12, 20), (24, 40), (7, 13), (6, 10)):
+        np.testing.assert_allclose(O.resize_bilinear_legacy(x, oh, ow).numpy(), X.resize_bilinear(x.numpy(), oh, ow), rtol=1e-5, atol=1e-6)
+    beta = _rnd(6, 4)
+    np.testing.assert_allclose(O.batchnorm_train(x, beta, 1e-3).numpy(), X.batch_norm_train(x.numpy(), beta.numpy(), 1e-3), rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(O.maxpool(_rnd(7, 1, 7, 9, 3)).numpy(), X.max_pool_2x2(_rnd(7, 1, 7, 9, 3).numpy()))
+    y = _rnd(8, 2, 8, 12, 3)
+    np.testing.assert_array_equal(O.space_to_depth4(y).numpy(), X.space_to_depth(y.numpy(), 4))
+    np.testing.assert_array_equal(O.lrelu(x, 0.2).numpy(), X.leaky_relu(x.numpy(), 0.2))
