@@ -9,9 +9,11 @@ Differences forced by the environment, stated once:
     initialisation; training saves both a .pt file and a TF V2 bundle;
   * training data: --input_video_dir is read by a thread-pool loader with the reference's directory layout and
     augmentations (tecogan_b200/lib/dataloader.py::HRClipLoader, after lib/dataloader.py:147-273) instead of TF queue
-    runners; when the flag is empty, seeded synthetic HR clips stand in; the device half (Gaussian down-sampling, crops)
-    is the same either way;
+    runners; an empty flag raises as in the reference unless --synthetic_data is given (seeded synthetic HR clips and,
+    without --vgg_ckpt, a seeded random frozen VGG -- for benchmarks and tests only); the device half (Gaussian
+    down-sampling, crops) is the same either way;
   * --precision {bf16,fp32} selects tcgen05 tensor-core or fp32 CUDA-core convolutions for inference;
+    --train_precision {fp32,bf16} does the same for training (default fp32, the reference's arithmetic);
   * under `torchrun` each rank trains on its own clip shard with one NCCL all-reduce per step.
 """
 import argparse
@@ -38,7 +40,9 @@ FLAG_DEFS = [  # (name, type, default) -- reference main.py:32-103
     ('display_freq', int, 20), ('summary_freq', int, 100), ('save_freq', int, 10000), ('ratio', float, 0.01),
     ('Dt_mergeDs', bool, True), ('Dt_ratio_0', float, 1.0), ('Dt_ratio_add', float, 0.0), ('Dt_ratio_max', float, 1.0),
     ('Dbalance', float, 0.4), ('crop_dt', float, 0.75), ('D_LAYERLOSS', bool, True),
-    ('precision', str, 'bf16'),   # extension
+    ('precision', str, 'bf16'),          # extension: inference arithmetic (bf16 tcgen05 | fp32 CUDA cores)
+    ('train_precision', str, 'fp32'),    # extension: training convolutions (fp32 as the reference | bf16 tcgen05)
+    ('synthetic_data', bool, False),     # extension: seeded synthetic HR clips / random frozen VGG instead of raising
 ]
 
 
@@ -90,8 +94,23 @@ def load_checkpoint(store, spec, num_resblock, need_d=False, need_vgg=False, pre
         store.load({k: torch.from_numpy(v) for k, v in got.items()})
     else:
         blob = torch.load(spec, map_location='cpu')      # variables only: optimiser slots / counters go through restore_train_state
-        store.load({k: v for k, v in blob.items() if not (k.endswith('/Adam') or k.endswith('/Adam_1') or k == 'global_step'
-                                                          or k.startswith('teco_b200/'))})
+        blob = {k: v for k, v in blob.items() if not (k.endswith('/Adam') or k.endswith('/Adam_1') or k == 'global_step'
+                                                      or k.startswith('teco_b200/'))}
+        # same strictness as Saver.restore / the TF branch above: every variable of this graph, with the right shape
+        shapes = variable_shapes(num_resblock, need_d, False)
+        for k, shp in shapes.items():
+            if k in blob and tuple(blob[k].shape) != tuple(shp):
+                raise ValueError('Wrong shape in for {} in ckpt,expected {}, got {}.'.format(k, str(tuple(shp)), str(tuple(blob[k].shape))))
+        missing = [k for k in shapes if k not in blob]
+        if missing and pre_trained_model:   # lib/ops.py:370-391: generator/fnet variables absent from the file are zero-filled
+            for k in missing:
+                if not k.startswith('tdiscriminator/'):
+                    blob[k] = torch.zeros(shapes[k])
+            print('Prepare to load %d weights from the pre-trained model (%d not in the file)' % (len(blob), len(missing)))
+        elif missing:
+            raise ValueError('checkpoint %s lacks %d variables of this graph (num_resblock=%d%s), e.g. %s'
+                             % (spec, len(missing), num_resblock, ', discriminator' if need_d else '', missing[:3]))
+        store.load(blob)
     if need_vgg and vgg_ckpt is not None:
         load_vgg_checkpoint(store, vgg_ckpt)
 
@@ -212,6 +231,11 @@ def synthetic_hr_batch(FLAGS, step, rank, device):
 
 
 def train(FLAGS):
+    if not FLAGS.input_video_dir and not FLAGS.synthetic_data:
+        raise ValueError('Video input directory input_video_dir is not provided')       # reference lib/dataloader.py:159-160
+    if FLAGS.vgg_scaling > 0 and FLAGS.vgg_ckpt is None and not FLAGS.synthetic_data:
+        raise ValueError('vgg_scaling > 0 needs --vgg_ckpt (the reference always restores vgg_19.ckpt, main.py:322-343); '
+                         'pass --synthetic_data to run on a seeded random frozen VGG')
     import torch
     import torch.distributed as dist
     from tecogan_b200 import variables as V
@@ -223,7 +247,7 @@ def train(FLAGS):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from tecogan_b200 import config
-    config.set_train_precision(FLAGS.precision)   # bf16: tcgen05 forward + input-gradient convs, fp32 master weights
+    config.set_train_precision(FLAGS.train_precision)   # fp32 as the reference; bf16: tcgen05 convolutions, fp32 master weights
     store = V.set_default_store(V.VariableStore(seed=FLAGS.rand_seed))   # same seed on every rank -> identical init
     gan = FLAGS.ratio > 0
     if FLAGS.checkpoint is not None:
@@ -232,39 +256,46 @@ def train(FLAGS):
     elif FLAGS.vgg_scaling > 0 and FLAGS.vgg_ckpt is not None:
         load_vgg_checkpoint(store, FLAGS.vgg_ckpt)
     elif FLAGS.vgg_scaling > 0:
-        print('[main] --vgg_ckpt not given: VGG19 uses seeded random weights (frozen)')
+        print('[main] --synthetic_data: VGG19 uses seeded random weights (frozen) -- the perceptual loss is NOT the reference\'s')
     dev = torch.device('cuda', local_rank)
     if FLAGS.input_video_dir:
         # HR clips from disk (reference lib/dataloader.py:147-273): decoded + augmented on queue_thread host threads,
         # uploaded from pinned memory; LR synthesis and target crops happen on the device (frvsr_gpu_data_loader)
         from tecogan_b200.lib.dataloader import HRClipLoader
         loader = HRClipLoader(FLAGS, rank=rank, world=world)
-        clip_iter = loader.batches()
-        next_hr = lambda step: next(clip_iter).to(dev, non_blocking=True)
         if FLAGS.max_iter is None:            # reference main.py:370-375
             if FLAGS.max_epoch is None:
                 raise ValueError('one of max_epoch or max_iter should be provided')
             FLAGS.max_iter = FLAGS.max_epoch * loader.steps_per_epoch
     else:
-        next_hr = lambda step: synthetic_hr_batch(FLAGS, step, rank, dev)
-    lr0, tg0 = frvsr_gpu_data_loader(next_hr(0), FLAGS)
+        loader = None
+    # the graph is built on a shape-only batch (its values are never trained on); the data stream starts afterwards, at
+    # the restored global step, so a resumed run sees exactly the batches the uninterrupted run would have seen
+    B_, T_, S_ = FLAGS.batch_size, FLAGS.RNN_N, FLAGS.crop_size * 4 + 8
+    lr0, tg0 = frvsr_gpu_data_loader(torch.zeros((B_, T_, S_, S_, 3), device=dev), FLAGS)
     Net = TecoGAN(lr0, tg0, FLAGS) if gan else FRVSR(lr0, tg0, FLAGS)
     print('Finish building the network.')
     if FLAGS.checkpoint is not None and not FLAGS.pre_trained_model:
         print('Loading everything from the checkpoint to continue the training...')
         restore_train_state(Net.train, FLAGS.checkpoint)
+    start_step = Net.global_step()
+    if loader is not None:
+        clip_iter = loader.batches(start_step=start_step)
+        next_hr = lambda gstep: next(clip_iter).to(dev, non_blocking=True)
+    else:
+        next_hr = lambda gstep: synthetic_hr_batch(FLAGS, gstep, rank, dev)   # seeded by the GLOBAL step
     frame_len = (FLAGS.RNN_N * 2 - 1) if FLAGS.pingpang else FLAGS.RNN_N
     max_iter, start = FLAGS.max_iter, time.time()
     try:
-        for step in range(max_iter):
-            lr_, tg_ = frvsr_gpu_data_loader(next_hr(step), FLAGS)
+        for step in range(max(0, max_iter - start_step)):
+            lr_, tg_ = frvsr_gpu_data_loader(next_hr(start_step + step), FLAGS)
             res = Net.train(lr_, tg_)
             run_step = Net.global_step()
             if step == 0 and rank == 0:
                 print('Optimization starts!!!(Ctrl+C to stop, will try saving the last model...)')
             if (run_step % FLAGS.display_freq) == 0 and rank == 0:
                 rate = (step + 1) * FLAGS.batch_size * world / (time.time() - start)
-                remaining = (max_iter - step) * FLAGS.batch_size * world / rate
+                remaining = (max_iter - start_step - step) * FLAGS.batch_size * world / rate
                 print("progress  step %d  image/sec %0.1fx%02d  remaining %dh%dm" %
                       (run_step, rate, frame_len, remaining // 3600, (remaining % 3600) // 60))
                 print("global_step", run_step)
@@ -289,7 +320,8 @@ def train(FLAGS):
 
 def main(argv=None):
     FLAGS = parse_flags(argv)
-    os.environ.setdefault("CUDA_VISIBLE_DEVICES", FLAGS.cudaID) if 'LOCAL_RANK' not in os.environ else None
+    if 'LOCAL_RANK' not in os.environ:
+        os.environ["CUDA_VISIBLE_DEVICES"] = FLAGS.cudaID       # reference main.py:107: overwritten unconditionally
     if FLAGS.output_dir is None:
         raise ValueError('The output directory is needed')
     os.makedirs(FLAGS.output_dir, exist_ok=True)

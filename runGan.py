@@ -40,6 +40,8 @@ def run_train(cmd1):
         print("runGAN.py: finished...")
 
 
+TrainingDataPath = os.environ.get("TECO_TRAINING_DATA", "/mnt/netdisk/video_data/")   # reference runGan.py:135,274: "update the TrainingDataPath"
+
 if runcase == 0:
     print("case 0 downloads models/data with wget (reference runGan.py:41-65); there is no network here.")
 elif runcase == 1:   # inference a trained model
@@ -63,6 +65,8 @@ elif runcase == 3:   # Train TecoGAN -- flags of record reference runGan.py:142-
     train_dir = "ex_TecoGAN%s/" % now_str
     cmd1 = [sys.executable, MAIN, "--cudaID", "0", "--output_dir", train_dir, "--summary_dir", os.path.join(train_dir, "log/"),
             "--mode", "train", "--batch_size", "4", "--RNN_N", "10", "--movingFirstFrame", "--random_crop", "--crop_size", "32",
+            "--input_video_dir", TrainingDataPath, "--input_video_pre", "scene", "--str_dir", "2000", "--end_dir", "2250",
+            "--end_dir_val", "2290", "--max_frm", "119", "--queue_thread", "12",   # reference runGan.py:178-184 / 276-282
             "--learning_rate", "0.00005", "--decay_step", "500000", "--decay_rate", "1.0", "--stair", "--beta", "0.9",
             "--max_iter", "500000", "--save_freq", "10000", "--num_resblock", "16", "--vgg_scaling", "0.2",
             "--ratio", "0.01", "--Dt_mergeDs", "--Dt_ratio_max", "1.0", "--Dt_ratio_0", "1.0", "--Dt_ratio_add", "0.0",
@@ -77,6 +81,8 @@ elif runcase == 4:   # Train FRVSR -- flags of record reference runGan.py:250-28
     train_dir = "ex_FRVSR%s/" % now_str
     cmd1 = [sys.executable, MAIN, "--cudaID", "0", "--output_dir", train_dir, "--summary_dir", os.path.join(train_dir, "log/"),
             "--mode", "train", "--batch_size", "4", "--RNN_N", "10", "--movingFirstFrame", "--random_crop", "--crop_size", "32",
+            "--input_video_dir", TrainingDataPath, "--input_video_pre", "scene", "--str_dir", "2000", "--end_dir", "2250",
+            "--end_dir_val", "2290", "--max_frm", "119", "--queue_thread", "12",   # reference runGan.py:178-184 / 276-282
             "--learning_rate", "0.00005", "--decay_step", "500000", "--decay_rate", "1.0", "--stair", "--beta", "0.9",
             "--max_iter", "500000", "--save_freq", "10000", "--num_resblock", "10", "--ratio", "-0.01", "--nopingpang"] + extra
     run_train(cmd1)

@@ -36,8 +36,10 @@ constexpr int TILE_ROWS = 16;
 constexpr int HALO_ROWS = TILE_ROWS + 2;
 constexpr int CB = 64;                 // channels per K block = one 128-byte swizzled row
 constexpr int MAX_WST = 12;
+constexpr int MAX_HST = 4;             // halo ring depth: 2 when the input is L2-resident, up to 4 when it streams from HBM
 constexpr int NUM_EPI_WARPS = 8;       // two warps per TMEM lane quarter, each taking half of the output channels
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS + 32;   // + the output-store warp (staged epilogue)
+constexpr int STORE_WARP = 2 + NUM_EPI_WARPS;
 
 struct TcParams {
   int N, H, W, Cin, Cout;             // Cout = channel pitch of y / res / bias (all output channels)
@@ -98,9 +100,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -188,7 +196,7 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 // issuer and the epilogue warps work on three different tiles at the same time.
 // H1: single halo box per block, horizontal taps as 128-byte descriptor start offsets (see conv_tc_sw.cu)
 template <int MODE, int TPS, int J, int KS, int H1>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
                   const __grid_constant__ CUtensorMap tmap_r, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -198,19 +206,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   uint8_t* halo_base = smem;                                             // HST stages x 3 kx-copies
   uint8_t* w_base = smem + (size_t)p.HST * p.halo_stage_bytes;           // WST weight slabs
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)p.WST * p.w_slab_bytes);
-  uint64_t* halo_full = bars;                    // [2]
-  uint64_t* halo_empty = bars + 2;               // [2]
-  uint64_t* w_full = bars + 4;                   // [MAX_WST]
-  uint64_t* w_empty = bars + 4 + MAX_WST;        // [MAX_WST]
-  uint64_t* acc_full = bars + 4 + 2 * MAX_WST;   // [2]
+  uint64_t* halo_full = bars;                    // [MAX_HST]
+  uint64_t* halo_empty = bars + MAX_HST;         // [MAX_HST]
+  uint64_t* w_full = bars + 2 * MAX_HST;         // [MAX_WST]
+  uint64_t* w_empty = w_full + MAX_WST;          // [MAX_WST]
+  uint64_t* acc_full = w_empty + MAX_WST;        // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(acc_empty + 3);   // [Ncta]
-  uint64_t* res_full = acc_empty + 3 + 128;      // after 256 floats of bias
-  uint64_t* res_empty = res_full + 1;
-  // output / residual staging tiles: J x [128 pixels][128 B], SWIZZLE_128B image of the TMA box (64 ch, 8 px, 16 rows)
-  uint8_t* stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(res_empty + 2) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stage_res = stage_out + (size_t)J * 16384;
+  uint64_t* res_full = acc_empty + 3 + 128;      // [2] after 256 floats of bias
+  uint64_t* stage_free = res_full + 2;           // [4] the TMA store of this staging tile has finished reading it
+  uint64_t* out_full = res_full + 6;             // [4] all epilogue warps have written their part of the staging tile
+  // Staged epilogue: two staging tiles (tile it uses it & 1), each J x [128 pixels][128 B] in the SWIZZLE_128B image of the
+  // TMA box (64 ch, 8 px, 16 rows).  A residual tile is TMA-loaded INTO the staging tile and the epilogue adds in place
+  // (same thread, same address), so residual and output share one buffer and both are double-buffered.
+  // Transposed conv (MODE 1, J == 1): four staging tiles, one per output phase (each the 16x8 pixels of that phase).
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(res_full + 10) + 1023) & ~(uintptr_t)1023);
 
   // work assignment: grid = nsplit x G CTAs; CTA c of a split owns tiles c, c+G, ...
   const int c_in_split = blockIdx.x % p.G;
@@ -234,8 +245,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), NUM_EPI_WARPS);
     }
-    mbar_init(smem_u32(res_full), 1);
-    mbar_init(smem_u32(res_empty), NUM_EPI_WARPS);
+    for (int i = 0; i < 4; ++i) {
+      if (i < 2) mbar_init(smem_u32(&res_full[i]), 1);
+      mbar_init(smem_u32(&stage_free[i]), 1);
+      mbar_init(smem_u32(&out_full[i]), NUM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_y) : "memory");
@@ -330,13 +344,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         __syncwarp();
         if (++hs == p.HST) { hs = 0; hph ^= 1; }
       }
-      if (p.tma_res) {   // residual tile(s) of this output tile, after its halo so that the halo prefetch never waits on the epilogue: free once the epilogue of the previous tile has read them
+      if (p.tma_res) {   // residual tile(s) of this output tile straight into staging tile it & 1: free once the store of tile it - 2 has read it
+        const int sg = it & 1;
         if (lane == 0) {
-          mbar_wait(smem_u32(res_empty), (uint32_t)((it & 1) ^ 1));
-          mbar_expect_tx(smem_u32(res_full), (uint32_t)(J * 16384));
+          mbar_wait(smem_u32(&stage_free[sg]), (uint32_t)(((it >> 1) & 1) ^ 1));
+          mbar_expect_tx(smem_u32(&res_full[sg]), (uint32_t)(J * 16384));
         }
         __syncwarp();
-        if (lane < J) tma_load_4d(smem_u32(stage_res + (size_t)lane * 16384), &tmap_r, smem_u32(res_full), n0, x0 + 8 * lane, y0, n);
+        if (lane < J)
+          tma_load_4d(smem_u32(stage_base + (size_t)(sg * J + lane) * 16384), &tmap_r, smem_u32(&res_full[sg]), n0, x0 + 8 * lane, y0, n);
       }
     }
     if (my_tiles == 0 && p.mcast && lane == 0) {
@@ -442,6 +458,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       if (lane == 0) TSTAMP(it, 1);
       __syncwarp();
     }
+  } else if (warp == STORE_WARP) {
+    // ===================== output store (staged epilogue only) =====================
+    if (MODE == 0 && p.tma_out && lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        int n, y0, x0;
+        tile_coords(it, n, y0, x0);
+        const int sg = it & 1;
+        mbar_wait(smem_u32(&out_full[sg]), (uint32_t)((it >> 1) & 1));   // every epilogue warp has fenced and arrived
+        for (int j = 0; j < J; ++j) tma_store_4d(&tmap_y, smem_u32(stage_base + (size_t)(sg * J + j) * 16384), n0, x0 + 8 * j, y0, n);
+        bulk_commit();
+        bulk_wait_read();                                                 // the staging tile may be overwritten again
+        mbar_arrive(smem_u32(&stage_free[sg]));
+      }
+    }
+    if (MODE == 1 && p.tma_out && lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        int n, y0, x0;
+        tile_coords(it, n, y0, x0);
+        for (int ph = 0; ph < 4; ++ph) {   // one 16x8-pixel box per sub-pixel phase through the 5-D map {C, px, x, py, n*H + y}
+          mbar_wait(smem_u32(&out_full[ph]), (uint32_t)(it & 1));
+          tma_store_5d(&tmap_y, smem_u32(stage_base + (size_t)ph * 16384), n0, ph & 1, x0, ph >> 1, n * p.H + y0);
+          bulk_commit();
+          bulk_wait_read();
+          mbar_arrive(smem_u32(&stage_free[ph]));
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9) =====================
     for (int c = (int)threadIdx.x - 64; c < p.Ncta; c += 32 * NUM_EPI_WARPS) s_bias[c] = p.bias ? p.bias[n0 + c] : 0.f;
@@ -512,58 +556,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 const float a = __uint_as_float(r[i]) + s_bias[c0 + i];
                 v[i] = fmaxf(a, a * act_slope);      // none: slope 1, relu: 0, lrelu: 0.2 -- no per-element branch
               }
-              if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop; rare (FNet head): keep it rolled
-#pragma unroll 1
+              if (p.act >= TECO_ACT_TANH24) {        // uniform, outside the element loop; rare (FNet head).  Unrolled: a rolled
+#pragma unroll                                       // loop indexes v[] dynamically and drags it into local memory for every layer
                 for (int i = 0; i < EW; ++i) v[i] = teco_act(v[i], p.act);
-              }
-              if (MODE == 0 && EW == 32 && p.tma_out) {
-                // c0 == 32 * chalf (Ncta == 64).  Pixel m owns row m of the staging tile; its 64 B are chunks 4*chalf..+3,
-                // XOR-swizzled with (m & 7) exactly like the TMA box -> conflict-free 16-byte accesses.
-                const uint32_t rowoff = (uint32_t)m * 128u;
-                if (j == 0) {
-                  // the previous tile's TMA store has finished reading the staging buffer (thread 64 waited before arriving)
-                  if (threadIdx.x == 64) bulk_wait_read();
-                  asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
-                  if (p.tma_res) mbar_wait_warp(smem_u32(res_full), (uint32_t)(it & 1));
-                }
-                if (p.tma_res) {
-                  const uint8_t* rs = stage_res + (size_t)j * 16384 + rowoff;
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(rs + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4));
-                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
-                      v[8 * k + 2 * i] += f.x;
-                      v[8 * k + 2 * i + 1] += f.y;
-                    }
-                  }
-                  if (j == J - 1) {
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(res_empty)) : "memory");
-                  }
-                }
-                uint8_t* os = stage_out + (size_t)j * 16384 + rowoff;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  uint32_t o[4];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
-                    o[i] = *reinterpret_cast<uint32_t*>(&h);
-                  }
-                  *reinterpret_cast<uint4*>(os + ((((uint32_t)(4 * chalf + k)) ^ ((uint32_t)m & 7u)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                continue;
               }
               if (!in_img) continue;
               if (p.out_f32) {
-#pragma unroll 1
+#pragma unroll
                 for (int i = 0; i < EW; ++i) {
-                  int c = n0 + c0 + i;
+                  const int c = n0 + c0 + i;
                   if (c < p.out_f32_c) {
-                    float a = v[i] + (p.res_f32 ? p.res_f32[pix * p.out_f32_c + c] : 0.f);
+                    const float a = v[i] + (p.res_f32 ? p.res_f32[pix * p.out_f32_c + c] : 0.f);
                     p.out_f32[pix * p.out_f32_c + c] = a * p.post_scale + p.post_shift;
                   }
                 }
@@ -599,14 +602,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
           }
         }
-        if (MODE == 0 && EW == 32 && p.tma_out) {
-          fence_async_smem();
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
-          if (threadIdx.x == 64) {
-            for (int j = 0; j < J; ++j) tma_store_4d(&tmap_y, smem_u32(stage_out + (size_t)j * 16384), n0, x0 + 8 * j, y0, n);
-            bulk_commit();
-          }
-        }
         if (threadIdx.x == 64) TSTAMP(it, 3);
         // warps with no channel step of their own (16-channel output stage: chalf == 1) still release the stage
         if (chalf * EW >= p.Ncta) {
@@ -614,9 +609,144 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
       }
     };
-    if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});   // (a single EW = 16 instantiation halves the SASS but
-    else run(std::integral_constant<int, 16>{});                   //  measured 7.4 us vs 6.9 us on the 64->64 layer)
-    if (p.tma_out && threadIdx.x == 64) bulk_wait_read();          // smem outlives the last store's reads; visibility comes with grid completion
+    if (MODE == 0 && p.tma_out) {
+      // ---- staged epilogue (Ncta == 64): this warp owns channels [32*chalf, +32) of pixel row m of every sub-tile.
+      // TMEM -> registers -> (+ bias, activation, + residual read from the staging tile) -> bf16 into the staging tile in
+      // place; the store warp sends the tile out.  The TMEM loads of sub-tile 1 are in flight while sub-tile 0 is
+      // processed (the epilogue was latency-bound: load -> wait -> math -> store per step, ~2300 clk per step).
+      constexpr bool PREF = (J == 2 && KS <= 2);
+      const uint32_t rowoff = (uint32_t)m * 128u, sw = (uint32_t)m & 7u;
+      float bias_r[32];      // this thread's 32 output channels: registers, not a shared-memory read per tile (the L1/smem
+#pragma unroll             // data pipe is what bounds this kernel: 48 operand wavefronts per N=64 MMA)
+      for (int i = 0; i < 32; ++i) bias_r[i] = s_bias[32 * chalf + i];
+      auto process = [&](uint32_t (&r)[KS][32], uint8_t* tile) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = __uint_as_float(r[0][i]);
+#pragma unroll
+          for (int k = 1; k < KS; ++k) a += __uint_as_float(r[k][i]);
+          a += bias_r[i];
+          v[i] = fmaxf(a, a * act_slope);      // none: slope 1, relu: 0, lrelu: 0.2 -- no per-element branch
+        }
+        uint8_t* row = tile + rowoff;   // (tanh/sigmoid layers never take the staged path: a rolled loop would put v[] in local memory)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4* cell = reinterpret_cast<uint4*>(row + ((((uint32_t)(4 * chalf + k)) ^ sw) << 4));   // XOR swizzle of the TMA box
+          if (p.tma_res) {
+            const uint4 rr = *cell;
+            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+              v[8 * k + 2 * i] += f.x;
+              v[8 * k + 2 * i + 1] += f.y;
+            }
+          }
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+            o[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *cell = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        const int as = (p.AS == 2) ? (it & 1) : 0;
+        const uint32_t ause = (uint32_t)((p.AS == 2) ? (it >> 1) : it);
+        const int sg = it & 1;
+        const uint32_t suse = (uint32_t)(it >> 1);
+        mbar_wait_warp(smem_u32(&acc_full[as]), ause & 1u);
+        tcgen05_fence_after();
+        if (threadIdx.x == 64 && it == 0) STAMP(6);
+        if (threadIdx.x == 64) TSTAMP(it, 2);
+        const uint32_t tb = tmem_base + (uint32_t)as * acc_stage_cols + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * chalf);
+        auto release_acc = [&]() {     // last TMEM read of this tile by this warp -> hand the stage back to the MMA issuer
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+        };
+        uint8_t* tile0 = stage_base + (size_t)(sg * J) * 16384;
+        uint32_t ra[KS][32];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) tmem_ld32(tb + (uint32_t)(k * 64), ra[k]);
+        tmem_wait_ld();
+        if (PREF) {
+          uint32_t rb[KS][32];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) tmem_ld32(tb + (uint32_t)((KS + k) * 64), rb[k]);
+          // the staging tile: residual landed (which implies it was free), or free of the store of tile it - 2
+          if (p.tma_res) mbar_wait_warp(smem_u32(&res_full[sg]), suse & 1u);
+          else mbar_wait_warp(smem_u32(&stage_free[sg]), (suse & 1u) ^ 1u);
+          process(ra, tile0);
+          tmem_wait_ld();
+          release_acc();
+          process(rb, tile0 + 16384);
+        } else {
+          if (J == 1) release_acc();
+          if (p.tma_res) mbar_wait_warp(smem_u32(&res_full[sg]), suse & 1u);
+          else mbar_wait_warp(smem_u32(&stage_free[sg]), (suse & 1u) ^ 1u);
+          process(ra, tile0);
+          if (J == 2) {
+#pragma unroll
+            for (int k = 0; k < KS; ++k) tmem_ld32(tb + (uint32_t)((KS + k) * 64), ra[k]);
+            tmem_wait_ld();
+            release_acc();
+            process(ra, tile0 + 16384);
+          }
+        }
+        fence_async_smem();            // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&out_full[sg]));
+        if (threadIdx.x == 64) TSTAMP(it, 3);
+      }
+    } else if (MODE == 1 && p.tma_out) {
+      // ---- staged epilogue of the transposed conv (J == 1, KS == 1, Ncta == 64): the four phase accumulators of the tile
+      // one after the other, the next phase's TMEM load in flight while this one is converted and written to its staging tile
+      const uint32_t rowoff = (uint32_t)m * 128u, sw = (uint32_t)m & 7u;
+      float bias_r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bias_r[i] = s_bias[32 * chalf + i];
+      for (int it = 0; it < my_tiles; ++it) {
+        const int as = (p.AS == 2) ? (it & 1) : 0;
+        const uint32_t ause = (uint32_t)((p.AS == 2) ? (it >> 1) : it);
+        mbar_wait_warp(smem_u32(&acc_full[as]), ause & 1u);
+        tcgen05_fence_after();
+        if (threadIdx.x == 64) TSTAMP(it, 2);
+        const uint32_t tb = tmem_base + (uint32_t)as * acc_stage_cols + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * chalf);
+        uint32_t r[2][32];
+        tmem_ld32(tb, r[0]);
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          tmem_wait_ld();
+          if (ph < 3) {
+            tmem_ld32(tb + (uint32_t)((ph + 1) * 64), r[(ph + 1) & 1]);
+          } else {
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+          }
+          mbar_wait_warp(smem_u32(&stage_free[ph]), (uint32_t)((it & 1) ^ 1));
+          uint8_t* row = stage_base + (size_t)ph * 16384 + rowoff;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float a0 = __uint_as_float(r[ph & 1][8 * k + 2 * i]) + bias_r[8 * k + 2 * i];
+              const float a1 = __uint_as_float(r[ph & 1][8 * k + 2 * i + 1]) + bias_r[8 * k + 2 * i + 1];
+              __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a0, a0 * act_slope), fmaxf(a1, a1 * act_slope));
+              o[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(row + ((((uint32_t)(4 * chalf + k)) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&out_full[ph]));
+        }
+        if (threadIdx.x == 64) TSTAMP(it, 3);
+      }
+    } else if (p.Ncta % 32 == 0) run(std::integral_constant<int, 32>{});   // (a single EW = 16 instantiation halves the SASS but
+    else run(std::integral_constant<int, 16>{});                           //  measured 7.4 us vs 6.9 us on the 64->64 layer)
   }
 
   if (threadIdx.x == 64) STAMP(7);
@@ -736,7 +866,13 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   const bool single_wave = tiles1 * p.nsplit <= (long long)sms;
   // Dispatch (same-box A/B, profiles/conv_tc_r01_notes.md): the one-tile-per-CTA kernel is faster for single-wave
   // launches and for the epilogue-heavy transposed conv (two CTAs per SM); this persistent kernel wins multi-wave convs.
-  if (single_wave || d->mode == 1) return teco_conv3x3_tc_one_tile(d, x, wpk, bias, res, y, res_f32, out_f32, stream);
+  // ... except large transposed convs (many waves): persistent CTAs with one staging tile per output phase
+  static const int env_tma = [] { const char* e = getenv("TECO_TC_TMA_EPI"); return e ? atoi(e) : 1; }();
+  static const int env_tp = [] { const char* e = getenv("TECO_TC_TCONV_PERSIST"); return e ? atoi(e) : 1; }();
+  const bool tconv_persist = env_tp && env_tma && d->mode == 1 && tiles1 >= 4LL * sms && p.nsplit == 1 && p.Ncta == 64 && y && !out_f32 &&
+                             !res && d->H % TILE_ROWS == 0 && d->W % 8 == 0 && d->act < TECO_ACT_TANH24 && p.nblk == 1;
+  if (single_wave || (d->mode == 1 && !tconv_persist))
+    return teco_conv3x3_tc_one_tile(d, x, wpk, bias, res, y, res_f32, out_f32, stream);
 
   // ---- configuration: (J, HST, weight staging, K-split, accumulator stages, grid)
   int J = 1;
@@ -796,6 +932,16 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
   p.copy_bytes = (uint32_t)(HALO_ROWS * (H1 ? 8 * J + 2 : 8 * J) * 128);
   p.halo_stage_bytes = H1 ? ((p.copy_bytes + 1023u) & ~1023u) : 3 * p.copy_bytes;
+  // Input larger than ~half of L2 streams from HBM: one tile of look-ahead (HST = 2) leaves the CTA waiting on DRAM
+  // latency (the 64->16 output stage at 296 x 128x128 ran 6300 clk per tile against ~2900 of work); use the shared memory
+  // the configuration leaves free for a deeper ring.
+  const bool tma_possible = tconv_persist || (env_tma && d->mode == 0 && y && !out_f32 && p.Ncta == 64 && d->act < TECO_ACT_TANH24);
+  const size_t staging_bytes = tconv_persist ? 1024 + (size_t)4 * 16384 : 1024 + (size_t)2 * J * 16384;
+  const double in_bytes = (double)d->N * d->H * d->W * d->Cin * 2.0;
+  if (!single_wave && p.nblk == 1 && in_bytes > 48e6) {
+    const size_t fixed = (size_t)p.WST * p.TPS * tap_bytes + (tma_possible ? staging_bytes : 0) + 8192;
+    while (p.HST < MAX_HST && fixed + (size_t)(p.HST + 1) * p.halo_stage_bytes <= 232448 - 2048) ++p.HST;
+  }
   const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
   p.w_slab_bytes = (uint32_t)(p.TPS * tap_bytes);
   p.KS = ks_force ? ks_force : ((p.TPS == 3 && d->mode == 0 && J * 3 * p.Ncta <= 512) ? 3 : 1);
@@ -806,13 +952,13 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   p.tmem_cols = tc;
   if (single_wave) p.G = (p.num_tiles + p.CS - 1) / p.CS * p.CS;   // padded to the cluster size
   else p.G = p.num_tiles < sms ? p.num_tiles : sms;
-  static const int env_tma = [] { const char* e = getenv("TECO_TC_TMA_EPI"); return e ? atoi(e) : 1; }();
-  p.tma_out = (env_tma && d->mode == 0 && y && !out_f32 && p.Ncta == 64) ? 1 : 0;
+  p.tma_out = tma_possible ? 1 : 0;
   p.tma_res = (p.tma_out && res) ? 1 : 0;
-  size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (4 + 2 * MAX_WST + 4 + 1) * 8 + 256 * sizeof(float) + 32 +
-                      (p.tma_out ? 1024 + (size_t)(1 + p.tma_res) * J * 16384 : 0);
-  if (smem_bytes > 226 * 1024 && p.tma_out) {   // no room for the staging tiles next to this configuration: direct stores
-    smem_bytes -= 1024 + (size_t)(1 + p.tma_res) * J * 16384;
+  size_t smem_bytes = 1024 + a_total + (size_t)p.WST * p.w_slab_bytes + (2 * MAX_HST + 2 * MAX_WST + 4 + 1) * 8 + 256 * sizeof(float) + 128 +
+                      (p.tma_out ? staging_bytes : 0);
+  if (smem_bytes > 232448 && p.tma_out) {       // 227 KB: the opt-in maximum of dynamic shared memory per block on sm_100
+    TECO_CHECK_ARG(!tconv_persist, "teco_conv3x3_tc: persistent transposed conv does not fit in shared memory");
+    smem_bytes -= staging_bytes;
     p.tma_out = p.tma_res = 0;
   }
 
@@ -835,7 +981,21 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     return TECO_E_CUDA;
   }
   CUtensorMap tmap_y = tmap, tmap_r = tmap;   // placeholders when the staged epilogue is off
-  if (p.tma_out) {
+  if (p.tma_out && d->mode == 1) {
+    // output [N, 2H, 2W, C] as {C, px, x, py, n*H + y}: one box = the 16x8 pixels of one sub-pixel phase (H % 16 == 0, so a
+    // box never runs from one image into the next)
+    const cuuint64_t odim[5] = {(cuuint64_t)d->Cout, 2, (cuuint64_t)d->W, 2, (cuuint64_t)d->N * d->H};
+    const cuuint64_t ostr[4] = {(cuuint64_t)d->Cout * 2, (cuuint64_t)d->Cout * 4, (cuuint64_t)d->W * d->Cout * 4,
+                                (cuuint64_t)d->W * d->Cout * 8};
+    const cuuint32_t obox[5] = {64, 1, 8, 1, (cuuint32_t)TILE_ROWS};
+    const cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+    cr = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, y, odim, ostr, obox, estr5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      teco_set_error("teco_conv3x3_tc: cuTensorMapEncodeTiled (transposed-conv output) failed with CUresult %d", (int)cr);
+      return TECO_E_CUDA;
+    }
+  } else if (p.tma_out) {
     const cuuint64_t odim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     const cuuint64_t ostr[3] = {(cuuint64_t)d->Cout * 2, (cuuint64_t)d->W * d->Cout * 2, (cuuint64_t)d->H * d->W * d->Cout * 2};
     const cuuint32_t obox[4] = {64, 8, (cuuint32_t)TILE_ROWS, 1};
@@ -862,7 +1022,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     teco_set_error("teco_conv3x3_tc: no kernel instantiation for mode=%d TPS=%d J=%d KS=%d", d->mode, p.TPS, J, p.KS);
     return TECO_E_UNSUPPORTED;
   }
-  TECO_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
+  TECO_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   const unsigned ctas = (unsigned)(p.G * p.nsplit);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);

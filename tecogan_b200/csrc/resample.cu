@@ -321,6 +321,54 @@ __global__ void bicubic4_f32_kernel(const float* __restrict__ x, float* __restri
   }
 }
 
+// C == 3 fast path: one thread per (LR pixel, output sub-row): 16 LR pixels in, 4 HR pixels x RGB = 48 contiguous bytes
+// out (three float4 stores; a warp writes 1.5 KB contiguous).  Same association order as the generic kernel above
+// (vertical taps first, then horizontal), so the results are identical.
+__global__ void bicubic4_rgb_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int h, int w, int in_cpitch) {
+  const long long total = (long long)N * h * 4 * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int lx = (int)(i % w);
+    long long t = i / w;
+    const int Y = (int)(t % (4 * h));
+    const int n = (int)(t / (4 * h));
+    const int ly = Y >> 2;
+    float wy[4];
+    bicubic_w(Y & 3, wy);
+    const float* b = x + (long long)n * h * w * in_cpitch;
+    float col[4][3];
+#pragma unroll
+    for (int bj = 0; bj < 4; ++bj) {
+      const int xx = min(max(lx - 1 + bj, 0), w - 1);
+      col[bj][0] = col[bj][1] = col[bj][2] = 0.f;
+#pragma unroll
+      for (int bi = 0; bi < 4; ++bi) {
+        const int yy = min(max(ly - 1 + bi, 0), h - 1);
+        const float* px = b + ((long long)yy * w + xx) * in_cpitch;
+        col[bj][0] += wy[bi] * px[0];
+        col[bj][1] += wy[bi] * px[1];
+        col[bj][2] += wy[bi] * px[2];
+      }
+    }
+    float o[12];
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      float wx[4];
+      bicubic_w(dx, wx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj) acc += wx[bj] * col[bj][c];
+        o[dx * 3 + c] = acc;
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(y + (((long long)n * 4 * h + Y) * (4 * w) + 4 * lx) * 3);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+  }
+}
+
 __global__ void resize_bilinear_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int h, int w, int C,
                                            int oh, int ow) {
   long long total = (long long)N * oh * ow * C;
@@ -583,6 +631,10 @@ int teco_upscale4_f32(const float* x, float* y, int32_t N, int32_t h, int32_t w,
 int teco_bicubic4_f32(const float* x, float* y, int32_t N, int32_t h, int32_t w, int32_t C, int32_t in_cpitch,
                       void* stream) {
   TECO_CHECK_ARG(x && y && N > 0 && h > 0 && w > 0 && C > 0 && in_cpitch >= C, "teco_bicubic4_f32: bad argument");
+  if (C == 3 && (((uintptr_t)y) & 15) == 0) {
+    LAUNCH1D(bicubic4_rgb_f32_kernel, (long long)N * h * w * 4, x, y, N, h, w, in_cpitch);
+    return TECO_OK;
+  }
   LAUNCH1D(bicubic4_f32_kernel, (long long)N * h * w * 16 * C, x, y, N, h, w, C, in_cpitch);
   return TECO_OK;
 }

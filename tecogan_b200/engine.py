@@ -247,3 +247,82 @@ class InferenceEngine:
             self.step(fr, next_lr=nxt)
             res.append((self.out01 if out == "f32" else self.out_u8).clone())
         return res
+
+
+class ClipEngine:
+    """B independent clips of T frames each (LR h x w), advanced in lock-step: the metric's workload ("10-frame clips",
+    BASELINE.json) and the shape of the reference's training recurrence (lib/Teco.py:102-164) used for inference.
+
+    All LR frames of a clip are known up front, so -- exactly as lib/Teco.py:102-117 does -- the flow of every
+    consecutive pair is estimated first (it depends on LR frames only, main.py:211); the generator recurrence
+    (main.py:212-216 per frame) then runs frame by frame with the batch of B clips as the GEMM M dimension.  The whole
+    clip batch is ONE CUDA graph replay; frame 0 of every clip starts from pre_warp = 0 (main.py:199).
+
+    run(lr_clip): lr_clip [T,B,h,w,3] fp32 in [0,1] (CUDA or pinned host, time-major so that a frame of all clips is one
+    contiguous block) -> self.clip_u8 [T,B,4h,4w,3] uint8 (save_img quantisation, lib/ops.py:521-523); the fp32 output of
+    the last frame stays in self.out01."""
+
+    def __init__(self, h, w, T, num_resblock=16, batch=1, use_graph=True, device="cuda"):
+        if h < 8 or w < 8:
+            raise ValueError("ClipEngine: LR frames must be at least 8x8")
+        if T < 1:
+            raise ValueError("ClipEngine: a clip has at least one frame")
+        if config.precision() != "bf16":
+            raise ValueError("ClipEngine runs the tcgen05 path; use InferenceEngine for the fp32 exact-parity mode")
+        self.h, self.w, self.T, self.B, self.nrb = h, w, T, batch, num_resblock
+        self.device = torch.device(device)
+        self.use_graph = use_graph
+        self.clip_in = torch.zeros((T, batch, h, w, 3), device=self.device, dtype=f32)
+        self.clip_u8 = torch.zeros((T, batch, 4 * h, 4 * w, 3), device=self.device, dtype=torch.uint8)
+        self.out01 = torch.zeros((batch, 4 * h, 4 * w, 3), device=self.device, dtype=f32)
+        with variable_scope('generator'), variable_scope('generator_unit') as gs:
+            _ensure_vars_generator(num_resblock)
+            self.gen = GeneratorPlan(gs, batch, h, w, num_resblock, self.device)
+        with variable_scope('fnet'), variable_scope('autoencode_unit') as fs:
+            _ensure_vars_fnet()
+            self.fnet = FNetPlan(fs, batch, h, w, self.device)
+        self.flows = torch.zeros((max(T - 1, 1),) + tuple(self.fnet.flow.shape), device=self.device, dtype=f32)
+        self.graph = None
+        # our kernel launches per clip batch: fnet pairs, then per frame warp/pack/generator/deprocess
+        self.launches = (T - 1) * (self.fnet.launches + 2) + T * (self.gen.launches + 2) + (T - 1)
+
+    def _body(self):
+        g, f, T = self.gen, self.fnet, self.T
+        for t in range(1, T):
+            _f32_slice_to_bf16(self.clip_in[t - 1], 0, 3, f.x_in, 0)
+            _f32_slice_to_bf16(self.clip_in[t], 0, 3, f.x_in, 3)
+            f.run(flow_out=self.flows[t - 1])
+        n = self.out01.numel()
+        for t in range(T):
+            if t == 0:
+                g.x_in[..., S2D_OFF:S2D_OFF + 48].zero_()
+            else:
+                K.warp_s2d_fused(g.out, self.flows[t - 1], g.x_in, S2D_OFF, in_scale=0.5, in_shift=0.5)
+            _f32_slice_to_bf16(self.clip_in[t], 0, 3, g.x_in, LR_OFF)
+            g.run(self.clip_in[t], 3)
+            call("teco_deprocess_u8", ptr(g.out, f32), ptr(self.out01, f32), ptr(self.clip_u8[t], torch.uint8), n, stream_ptr())
+
+    def replay(self):
+        """Process the clip batch already in self.clip_in."""
+        if not self.use_graph:
+            self._body()
+            return self.clip_u8
+        if self.graph is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()                      # eager warm-up (function attributes, allocator)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+        self.graph.replay()
+        return self.clip_u8
+
+    def run(self, lr_clip):
+        if tuple(lr_clip.shape) != tuple(self.clip_in.shape):
+            raise ValueError("ClipEngine.run: expected LR clips of shape %s (time-major), got %s"
+                             % (tuple(self.clip_in.shape), tuple(lr_clip.shape)))
+        self.clip_in.copy_(lr_clip, non_blocking=True)
+        return self.replay()

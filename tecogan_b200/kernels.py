@@ -565,7 +565,7 @@ def _pad64(c):
 
 
 def _tc_packed(w, b, flags, cin_pad, cout_pad):
-    key = (w.data_ptr(), flags)
+    key = (w.data_ptr(), tuple(w.shape), flags, cin_pad, cout_pad)   # (an address alone can be reused by another weight)
     hit = _tc_wcache.get(key)
     if hit is None:
         wpk = packed_weight(w.detach(), cin_pad, cout_pad, flags)

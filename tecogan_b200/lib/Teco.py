@@ -300,6 +300,7 @@ class _TrainState:
         self.counter1 = self.counter2 = 0
         self.last = None
         from .. import config
+        K.tc_cache_clear()                         # packed bf16 weights of a previous trainer are not ours
         prev_precision = config.precision()
         with torch.no_grad():                      # materialise every variable once (xavier / zeros / loaded values)
             config.set_precision("fp32")

@@ -190,9 +190,11 @@ class FNetPlan:
         self.flow = torch.zeros((n, ch, cw, 2), device=device, dtype=f32)
         self.launches = 14 + 6
 
-    def run(self):
+    def run(self, flow_out=None):
+        """flow_out: optional fp32 [n,fh,fw,2] destination (default self.flow)."""
         x = self.x_in
         n = self.n
+        flow = self.flow if flow_out is None else flow_out
         for i, ((c1, c2), (t1, t2, t3)) in enumerate(zip(self.layers, self.bufs)):
             K.conv3x3_tc(x, c1.wpk, c1.bias, t1, cout=c1.cout_pad, act=ACT_LRELU02)
             K.conv3x3_tc(t1, c2.wpk, c2.bias, t2, cout=c2.cout_pad, act=ACT_LRELU02)
@@ -203,8 +205,8 @@ class FNetPlan:
                 call("teco_resize2x_bf16", ptr(t2, bf16), ptr(t3, bf16), n, hh, ww, cc, stream_ptr())
             x = t3
         K.conv3x3_tc(x, self.l_o1.wpk, self.l_o1.bias, self.o1, cout=64, act=ACT_LRELU02)
-        K.conv3x3_tc(self.o1, self.l_o2.wpk, self.l_o2.bias, None, cout=16, act=ACT_TANH24, out_f32=self.flow)
-        return self.flow
+        K.conv3x3_tc(self.o1, self.l_o2.wpk, self.l_o2.bias, None, cout=16, act=ACT_TANH24, out_f32=flow)
+        return flow
 
 
 _plans = {}

@@ -264,7 +264,7 @@ def test_conv3x3_tc_matches_oracle_on_bf16_operands(n, h, w, cin, cout, act):
     assert_close(got, O.conv2d(x, wt, b) + res, 2e-3, 1.0 / 128, what="conv3x3_tc+res")
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 16, 8), (1, 32, 32), (2, 24, 20), (1, 64, 64)])
+@pytest.mark.parametrize("n,h,w", [(1, 16, 8), (1, 32, 32), (2, 24, 20), (1, 64, 64), (5, 128, 128), (40, 64, 64), (3, 144, 120)])
 def test_conv_transpose_tc_matches_oracle_on_bf16_operands(n, h, w):
     from tecogan_b200 import kernels as K
     x, wt, b = _bf(rnd(1, n, h, w, 64)), _bf(rnd(2, 3, 3, 64, 64) * 0.06), rnd(3, 64) * 0.1
@@ -284,6 +284,24 @@ def test_conv3x3_tc_fp32_output_stage():
     out = torch.zeros(1, 40, 24, 3, device="cuda")
     K.conv3x3_tc(dev(x).to(torch.bfloat16), wpk, K.pad_bias(dev(b), 16), cout=16, out_f32=out, res_f32=dev(bic), post=(2.0, -1.0))
     assert_close(out, ref, 1e-4, what="output stage")
+
+
+def test_conv3x3_tc_fp32_output_stage_streaming_from_hbm():
+    """The 64->3 output stage on an input larger than L2 (deep halo ring, many tiles per persistent CTA); checked against
+    the oracle on a few sampled images."""
+    from tecogan_b200 import kernels as K
+    n, h, w = 48, 128, 128                      # 48 x 128 x 128 x 64 ch bf16 = 100 MB
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(n, h, w, 64, generator=g).to(torch.bfloat16)
+    wt, b = _bf(rnd(2, 3, 3, 64, 3) * 0.05), rnd(3, 3) * 0.1
+    bic = torch.rand(n, h, w, 3, generator=g)
+    wpk = K.packed_weight(dev(wt), 64, 16)
+    out = torch.zeros(n, h, w, 3, device="cuda")
+    K.conv3x3_tc(x.cuda(), wpk, K.pad_bias(dev(b), 16), cout=16, out_f32=out, res_f32=bic.cuda(), post=(2.0, -1.0))
+    torch.cuda.synchronize()
+    for i in (0, 17, 47):
+        ref = (O.conv2d(x[i:i + 1].float(), wt, b) + bic[i:i + 1]) * 2 - 1
+        assert_close(out[i:i + 1], ref, 1e-4, what="output stage image %d" % i)
 
 
 def test_abi_rejects_bad_arguments_with_valueerror():

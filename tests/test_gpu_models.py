@@ -220,3 +220,88 @@ def test_fnet_lookahead_is_bit_identical_to_the_serial_recurrence():
         assert torch.equal(out, serial[i]), i
     with pytest.raises(ValueError):
         eng.step(frames[0], next_lr=torch.zeros(8, 8, 3, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Parity at the BENCHMARKED shapes (bench.py): the metric config (lock-step batch of 10-frame 32x32 clips through
+# ClipEngine), configs[1] (128x128 streaming with the look-ahead graph) and one config-5 batch (256x256 x b2).
+def _smooth_clips(T, B, h, w, seed):
+    import bench
+    return bench.synthetic_clips(T, B, h, w, seed)
+
+
+def _y_psnr_delta(frames_lr, ours01, ref01):
+    """|Y-PSNR(target, ours) - Y-PSNR(target, oracle)| with the reference's metric (metrics.py:37-70) against a common
+    stand-in target (bicubic_four of the LR frame; no HR ground truth is shipped)."""
+    d = []
+    for lr, o, r in zip(frames_lr, ours01, ref01):
+        tgt = O.save_img_u8(O.bicubic_four(lr.unsqueeze(0))[0])
+        d.append(abs(O.psnr_y(tgt, O.save_img_u8(o)) - O.psnr_y(tgt, O.save_img_u8(r))))
+    return max(d)
+
+
+def test_metric_config_clip_engine_matches_oracle_and_streaming_engine():
+    """bench.py headline path: B clips x 10 frames 32x32 in lock-step, one CUDA graph, fnet for all pairs first."""
+    from tecogan_b200 import config
+    from tecogan_b200.engine import ClipEngine, InferenceEngine
+    T, B, N = 10, 6, 16
+    pg, pf = O.damp_generator(O.init_generator(seed=1234, num_resblock=N)), O.init_fnet(seed=4321)
+    clips = _smooth_clips(T, B, 32, 32, seed=3)
+    _fresh_store({**pg, **pf})
+    config.set_precision("bf16")
+    eng = ClipEngine(32, 32, T, N, batch=B)
+    u8 = eng.run(clips.cuda()).clone()
+    u8_again = eng.run(clips.cuda()).clone()            # second replay of the captured graph: same bits
+    assert torch.equal(u8, u8_again)
+    eager = ClipEngine(32, 32, T, N, batch=B, use_graph=False).run(clips.cuda())
+    assert torch.equal(u8, eager)
+    # same kernels as the streaming engine at the same batch -> bit-identical frames
+    stream = InferenceEngine(32, 32, N, batch=B).run_sequence([clips[t].cuda() for t in range(T)], out="u8")
+    for t in range(T):
+        assert torch.equal(u8[t], stream[t]), t
+    # against the oracle, clip by clip (fp32 CPU restatement of main.py:253-268)
+    worst_psnr, worst_dy = 1e9, 0.0
+    for b in range(3):
+        ref = O.inference_sequence(pg, pf, [clips[t, b] for t in range(T)], N)
+        ours = [u8[t, b].cpu().float() / 255.0 for t in range(T)]
+        refq = [O.save_img_u8(r).astype(np.float32) / 255.0 for r in ref]
+        worst_psnr = min(worst_psnr, min(O.psnr(o.numpy(), r) for o, r in zip(ours, refq)))
+        worst_dy = max(worst_dy, _y_psnr_delta([clips[t, b] for t in range(T)], ours, ref))
+    assert worst_psnr > 40.0, worst_psnr
+    assert worst_dy < 0.05, worst_dy
+
+
+def test_configs1_128x128_lookahead_graph_32_frames_matches_oracle():
+    """bench.py configs[1] path: bf16, 128x128 -> 512x512, look-ahead CUDA graph on two streams, 32 recurrent frames."""
+    from tecogan_b200 import config
+    from tecogan_b200.engine import InferenceEngine
+    T, N = 32, 16
+    pg, pf = O.damp_generator(O.init_generator(seed=1234, num_resblock=N)), O.init_fnet(seed=4321)
+    clip = _smooth_clips(T, 1, 128, 128, seed=0)[:, 0]
+    frames = [clip[t] for t in range(T)]
+    ref = O.inference_sequence(pg, pf, frames, N)
+    _fresh_store({**pg, **pf})
+    config.set_precision("bf16")
+    outs = InferenceEngine(128, 128, N, use_graph=True).run_sequence([f.cuda() for f in frames], lookahead=True)
+    ours = [o[0].cpu() for o in outs]
+    ps = [O.psnr(o.numpy(), r.numpy()) for o, r in zip(ours, ref)]
+    assert min(ps) > 40.0, ps
+    assert _y_psnr_delta(frames, ours, ref) < 0.05
+
+
+def test_config5_256x256_batch2_matches_oracle():
+    """bench.py config-5 path: ClipEngine at 256x256 -> 1024x1024, two clips, three frames (persistent multi-tile convs)."""
+    from tecogan_b200 import config
+    from tecogan_b200.engine import ClipEngine
+    T, B, N = 3, 2, 16
+    pg, pf = O.damp_generator(O.init_generator(seed=1234, num_resblock=N)), O.init_fnet(seed=4321)
+    clips = _smooth_clips(T, B, 256, 256, seed=5)
+    _fresh_store({**pg, **pf})
+    config.set_precision("bf16")
+    u8 = ClipEngine(256, 256, T, N, batch=B).run(clips.cuda())
+    ref = O.inference_sequence(pg, pf, [clips[t, 1] for t in range(T)], N)
+    ours = [u8[t, 1].cpu().float() / 255.0 for t in range(T)]
+    refq = [O.save_img_u8(r).astype(np.float32) / 255.0 for r in ref]
+    ps = [O.psnr(o.numpy(), r) for o, r in zip(ours, refq)]
+    assert min(ps) > 40.0, ps
+    assert _y_psnr_delta([clips[t, 1] for t in range(T)], ours, ref) < 0.05

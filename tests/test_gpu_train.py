@@ -242,3 +242,56 @@ def test_checkpoint_resume_restores_everything(tmp_path, fmt):
             assert d.max().item() < 2.0 * lr and (d < 0.05 * lr).float().mean().item() > 0.97, (k, d.max().item())
     assert abs(net2.train.tb_ema - want_tb) < 1e-6
     np.testing.assert_allclose(np.array(net2.train.loss_ema), np.array(want_ema), rtol=1e-4, atol=1e-7)
+
+
+def _config3_case():
+    """BASELINE configs[2] shape: FRVSR (runGan.py case 4), B=4 clips x RNN_N=10 frames, 32x32 LR crops, N=10 blocks."""
+    FL = O.TrainFlags.frvsr(batch_size=4, crop_size=32, RNN_N=10, num_resblock=10)
+    P = {}
+    P.update(O.damp_generator(O.init_generator(seed=161, num_resblock=10, bias_std=0.02)))
+    P.update(O.init_fnet(seed=171, bias_std=0.02))
+    g = torch.Generator().manual_seed(5)
+    ri = torch.rand(4, 10, 32, 32, 3, generator=g)
+    rt = torch.rand(4, 10, 128, 128, 3, generator=g) * 2 - 1
+    return FL, P, ri, rt
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config3_shape_train_step_matches_oracle(precision):
+    """The benchmarked training shape (bench.py train.config3_frvsr): loss scalars and every gradient of one step against
+    the oracle Trainer.  fp32: loss rtol 1e-3, per-tensor gradient error <= 1e-2 of the tensor's max (10 recurrent frames
+    of BPTT, atomically accumulated weight gradients).  bf16 tensor-core convolutions: loss rtol 3e-2, gradient cosine
+    > 0.98 per network."""
+    from tecogan_b200 import config
+    from tecogan_b200.lib.Teco import FRVSR
+    FL, P, ri, rt = _config3_case()
+    tr = O.Trainer(P, FL, False)
+    ref = tr.step(ri, rt)
+    _fresh_store(P)
+    config.set_train_precision(precision)
+    try:
+        net = FRVSR(ri.cuda(), rt.cuda(), FL)
+        out = net.train()
+    finally:
+        config.set_train_precision("fp32")
+    want = np.array([float(v) for v in ref["update_list"]])
+    st = net.train
+    if precision == "fp32":
+        np.testing.assert_allclose(np.array(out["update_list"]), want, rtol=1e-3, atol=2e-5)
+        o = 0
+        for k in st.names:
+            n = st.store[k].numel()
+            got, w = st.bucket[o:o + n].cpu(), ref["grads"][k].reshape(-1)
+            err = (got - w).abs().max().item() / max(w.abs().max().item(), 1e-6)
+            assert err < 1e-2, (k, err)
+            o += n
+    else:
+        np.testing.assert_allclose(np.array(out["update_list"]), want, rtol=3e-2, atol=1e-4)
+        o = 0
+        for names in (st.opt_g.names, st.opt_f.names):
+            n = sum(st.store[k].numel() for k in names)
+            got = st.bucket[o:o + n].cpu()
+            refg = torch.cat([ref["grads"][k].reshape(-1) for k in names])
+            cos = float((got * refg).sum() / (got.norm() * refg.norm()))
+            assert cos > 0.98, (names[0], cos)
+            o += n

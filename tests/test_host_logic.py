@@ -109,3 +109,39 @@ def test_two_rank_gloo_allreduce_bucket_and_identical_control_flow():
     np.testing.assert_array_equal(b0, b1)                    # every rank holds the same reduced bucket
     assert d0 == d1 and e0 == e1                             # hence the same with-D / without-D branch every step
     assert d0 == [True, False, False]                        # EMA(0.01 * 0.5) crosses Dbalance=0.004 after one update
+
+
+def test_pt_checkpoint_is_validated_like_saver_restore(tmp_path):
+    """A .pt checkpoint must hold every variable of the graph with the right shape (Saver.restore semantics,
+    reference main.py:221-224,245,346-349); --pre_trained_model zero-fills missing generator/fnet variables
+    (lib/ops.py:370-391) and leaves discriminator variables to their initialiser."""
+    import main
+    from tecogan_b200 import variables as V
+    from tecogan_b200.init_params import xavier_params
+    p10 = xavier_params(3, num_resblock=10)
+    path = str(tmp_path / "m10.pt")
+    torch.save(p10, path)
+    st = V.VariableStore(device="cpu")
+    main.load_checkpoint(st, path, 10)
+    assert set(st) == set(p10)
+    with pytest.raises(ValueError, match="lacks"):
+        main.load_checkpoint(V.VariableStore(device="cpu"), path, 16)                 # a 10-block file for a 16-block graph
+    with pytest.raises(ValueError, match="lacks"):
+        main.load_checkpoint(V.VariableStore(device="cpu"), path, 10, need_d=True)    # FRVSR file where D weights are expected
+    st2 = V.VariableStore(device="cpu")
+    main.load_checkpoint(st2, path, 16, need_d=True, pre_trained_model=True)
+    assert float(st2['generator/generator_unit/resblock_16/conv_2/Conv/weights'].abs().max()) == 0.0
+    assert not any(k.startswith('tdiscriminator/') for k in st2)
+    bad = dict(p10)
+    bad['fnet/autoencode_unit/encoder_1/conv_1/Conv/weights'] = torch.zeros(3, 3, 6, 16)
+    torch.save(bad, path)
+    with pytest.raises(ValueError, match="Wrong shape"):
+        main.load_checkpoint(V.VariableStore(device="cpu"), path, 10)
+
+
+def test_train_mode_refuses_to_run_without_data_or_vgg_unless_opted_in():
+    import main
+    F = main.parse_flags(["--mode", "train", "--output_dir", "/tmp/x"])
+    assert F.train_precision == "fp32" and F.synthetic_data is False
+    with pytest.raises(ValueError, match="input_video_dir is not provided"):
+        main.train(F)
