@@ -171,6 +171,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
@@ -269,10 +274,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) STAMP(1);
 
-  constexpr int nacc = MODE == 1 ? 4 : 1;
+  // MODE 2 ("kx-fused" conv for a narrow output: Cout padded to 16): ONE tcgen05.mma covers the three horizontal taps of a
+  // kernel row -- B = [3 taps x Ncta] rows (the packed slab of row ky as it is), N = 3*Ncta, A = the halo pixels of the
+  // sub-tile WITHOUT a horizontal shift.  D block kx at halo column c then holds tap kx's contribution to output column
+  // c - kx, and the epilogue forms out(x) = D0(x) + D1(x+1) + D2(x+2) with warp shuffles.  A tile is 8J halo columns wide and
+  // yields 8J-2 output columns.  Why: an MMA costs ~60 clk whatever N is (the 4 KB A tile read bounds it), so the 64->3
+  // output stage at HR resolution used to cost as much per pixel as a 64->64 layer; this needs 12 MMAs per sub-tile, not 36.
+  constexpr int nacc = MODE == 1 ? 4 : (MODE == 2 ? 3 : 1);
   constexpr int ncopies = H1 ? 1 : (MODE == 1 ? 2 : 3);   // horizontal tap offsets that occur (tconv only reads x-1, x)
   constexpr int slabs_per_blk = 9 / TPS;
-  constexpr int row_bytes = (H1 ? 8 * J + 2 : 8 * J) * 128;   // one box row (pixels x 128 B)
+  constexpr int row_bytes = ((H1 && MODE != 2) ? 8 * J + 2 : 8 * J) * 128;   // one box row (pixels x 128 B)
+  constexpr int tile_w = MODE == 2 ? 8 * J - 2 : 8 * J;                      // output columns per tile
   constexpr uint32_t copy_bytes = (uint32_t)(HALO_ROWS * row_bytes);
   const int slabs_per_tile = slabs_per_blk * p.nblk;
   const uint32_t acc_stage_cols = (uint32_t)(J * nacc * KS * p.Ncta);   // TMEM columns of one accumulator stage
@@ -283,7 +295,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     tile /= p.tiles_x;
     const int ty = tile % p.tiles_y;
     n = tile / p.tiles_y;
-    x0 = tx * 8 * J;
+    x0 = tx * tile_w;
     y0 = ty * TILE_ROWS;
   };
 
@@ -389,7 +401,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           }
           tcgen05_fence_after();
           if (lane == 0 && b == 0 && it == 0) STAMP(16 + g);
-          {
+          if (MODE == 2) {
+            const uint32_t slab_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
+            const uint64_t a_row = umma_desc_sw128(halo_addr, a_sbo) + (uint64_t)((uint32_t)(g * row_bytes) >> 4);
+            const uint64_t b3 = umma_desc_sw128(slab_addr, b_sbo);
+            const uint32_t idesc3 = umma_idesc(3 * p.Ncta);
+            const uint32_t first = (b == 0 && g == 0) ? 1u : 0u;
+            if (elect_one()) {
+#pragma unroll
+              for (int s = 0; s < CB / 16; ++s)
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                  umma_bf16(tmem_acc + (uint32_t)(j * 3) * (uint32_t)p.Ncta, a_row + (uint32_t)((j * 1024 + s * 32) >> 4),
+                            b3 + (uint32_t)((s * 32) >> 4), idesc3, (first && s == 0) ? 0u : 1u);
+            }
+            __syncwarp();
+          } else {
             // Whole (converged) warp computes the warp-uniform bases; one elected lane issues the unrolled MMA stream.
             const uint32_t slab_addr = smem_u32(w_base + (size_t)ws * p.w_slab_bytes);
             const uint64_t a_base = umma_desc_sw128(halo_addr, a_sbo);
@@ -700,6 +727,60 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         if (lane == 0) mbar_arrive(smem_u32(&out_full[sg]));
         if (threadIdx.x == 64) TSTAMP(it, 3);
       }
+    } else if (MODE == 2) {
+      // ---- kx-fused narrow output stage (fp32 output, <= 4 channels): out(x) = D0(x) + D1(x+1) + D2(x+2)
+      const int C = p.out_f32_c;
+      for (int it = 0; it < my_tiles; ++it) {
+        int n, y0, x0;
+        tile_coords(it, n, y0, x0);
+        const int as = (p.AS == 2) ? (it & 1) : 0;
+        const uint32_t ause = (uint32_t)((p.AS == 2) ? (it >> 1) : it);
+        mbar_wait_warp(smem_u32(&acc_full[as]), ause & 1u);
+        tcgen05_fence_after();
+        if (threadIdx.x == 64) TSTAMP(it, 2);
+        const uint32_t tb = tmem_base + (uint32_t)as * acc_stage_cols + ((uint32_t)(32 * q) << 16);
+        uint32_t d[J][3][4];
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) tmem_ld4(tb + (uint32_t)((j * 3 + kx) * p.Ncta), d[j][kx]);
+        tmem_wait_ld();
+        tcgen05_fence_before();
+        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+        const int oy = y0 + ry;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          float v[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            // neighbours one and two halo columns to the right: the same sub-tile (lane + 1, + 2) or the next one (lane - 7, - 6)
+            const float s1 = __shfl_sync(0xffffffffu, __uint_as_float(d[j][1][c]), (lane + 1) & 31);
+            const float s2 = __shfl_sync(0xffffffffu, __uint_as_float(d[j][2][c]), (lane + 2) & 31);
+            float n1 = 0.f, n2 = 0.f;
+            if (j + 1 < J) {
+              n1 = __shfl_sync(0xffffffffu, __uint_as_float(d[j + 1 < J ? j + 1 : j][1][c]), (lane - 7) & 31);
+              n2 = __shfl_sync(0xffffffffu, __uint_as_float(d[j + 1 < J ? j + 1 : j][2][c]), (lane - 6) & 31);
+            }
+            const float a = __uint_as_float(d[j][0][c]) + (rx < 7 ? s1 : n1) + (rx < 6 ? s2 : n2) + s_bias[c];
+            v[c] = fmaxf(a, a * act_slope);
+          }
+          if (p.act >= TECO_ACT_TANH24) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = teco_act(v[c], p.act);
+          }
+          const int tc = 8 * j + rx, ox = x0 + tc;
+          // the two warps of a lane quarter take alternate sub-tiles (no early exit: the shuffles above are warp-collective)
+          const bool mine = ((warp - 2) >> 2) == (j & 1) && tc < tile_w && ox < p.W && oy < p.H;
+          const size_t pix = ((size_t)n * p.H + oy) * p.W + ox;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (mine && c < C) {
+              const float a = v[c] + (p.res_f32 ? p.res_f32[pix * C + c] : 0.f);
+              p.out_f32[pix * C + c] = a * p.post_scale + p.post_shift;
+            }
+        }
+        if (threadIdx.x == 64) TSTAMP(it, 3);
+      }
     } else if (MODE == 1 && p.tma_out) {
       // ---- staged epilogue of the transposed conv (J == 1, KS == 1, Ncta == 64): the four phase accumulators of the tile
       // one after the other, the next phase's TMEM load in flight while this one is converted and written to its staging tile
@@ -926,11 +1007,24 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
     const size_t stage2 = ((size_t)HALO_ROWS * 18 * 128 + 1023) & ~(size_t)1023;
     if (2 * stage2 + 9 * tap_bytes * p.nblk <= budget) { J = 2; ks_force = 2; }
   }
+  // Narrow fp32 output stage (generator 64->3, fnet 32->2) on many tiles: the kx-fused kernel (MODE 2 above)
+  static const int env_kx = [] { const char* e = getenv("TECO_TC_KX"); return e ? atoi(e) : 1; }();
+  const bool kx = env_kx && H1 && !single_wave && d->mode == 0 && out_f32 && !y && !res && d->Cout == 16 && p.nsplit == 1 && p.nblk == 1 &&
+                  d->out_f32_c <= 4 && p.mcast && p.TPS == 3;
+  if (kx) {
+    double best = 0.0;
+    for (int jj = 2; jj <= 4; ++jj) {   // widest use of the 8*jj halo columns: W / (tiles * 8 jj)
+      const double eff = (double)d->W / ((double)teco_ceil_div(d->W, 8 * jj - 2) * 8 * jj);
+      if (eff > best + 1e-9) { best = eff; J = jj; }
+    }
+    ks_force = 1;
+  }
+  const int box_w = (H1 && !kx) ? 8 * J + 2 : 8 * J;
   p.J = J;
-  p.tiles_x = teco_ceil_div(d->W, 8 * J);
+  p.tiles_x = kx ? teco_ceil_div(d->W, 8 * J - 2) : teco_ceil_div(d->W, 8 * J);
   p.tiles_y = teco_ceil_div(d->H, TILE_ROWS);
   p.num_tiles = (int)((long long)d->N * p.tiles_x * p.tiles_y);
-  p.copy_bytes = (uint32_t)(HALO_ROWS * (H1 ? 8 * J + 2 : 8 * J) * 128);
+  p.copy_bytes = (uint32_t)(HALO_ROWS * box_w * 128);
   p.halo_stage_bytes = H1 ? ((p.copy_bytes + 1023u) & ~1023u) : 3 * p.copy_bytes;
   // Input larger than ~half of L2 streams from HBM: one tile of look-ahead (HST = 2) leaves the CTA waiting on DRAM
   // latency (the 64->16 output stage at 296 x 128x128 ran 6300 clk per tile against ~2900 of work); use the shared memory
@@ -945,7 +1039,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   const size_t a_total = (size_t)p.HST * p.halo_stage_bytes;
   p.w_slab_bytes = (uint32_t)(p.TPS * tap_bytes);
   p.KS = ks_force ? ks_force : ((p.TPS == 3 && d->mode == 0 && J * 3 * p.Ncta <= 512) ? 3 : 1);
-  const uint32_t stage_cols = (uint32_t)(J * nacc * p.KS * p.Ncta);
+  const uint32_t stage_cols = (uint32_t)(J * (kx ? 3 : nacc) * p.KS * p.Ncta);
   if (!single_wave && 2 * stage_cols <= 512) p.AS = 2;
   uint32_t cols = stage_cols * (uint32_t)p.AS, tc = 32;
   while (tc < cols) tc <<= 1;
@@ -970,7 +1064,7 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   CUtensorMap tmap;
   const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
   const cuuint64_t gstr[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(H1 ? 8 * J + 2 : 8 * J), (cuuint32_t)HALO_ROWS, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)box_w, (cuuint32_t)HALO_ROWS, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1013,10 +1107,11 @@ extern "C" int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void*
   using KernelT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
   KernelT kern = nullptr;
 #define TECO_PICK(M, T, JJ, K)                                              \
-  if (d->mode == M && p.TPS == T && J == JJ && p.KS == K)                   \
+  if ((kx ? 2 : d->mode) == M && p.TPS == T && J == JJ && p.KS == K)        \
     kern = H1 ? conv3x3_tc_kernel<M, T, JJ, K, 1> : conv3x3_tc_kernel<M, T, JJ, K, 0>;
   TECO_PICK(0, 3, 2, 2) TECO_PICK(0, 3, 1, 3) TECO_PICK(0, 3, 2, 3) TECO_PICK(0, 3, 1, 1) TECO_PICK(0, 3, 2, 1) TECO_PICK(0, 1, 1, 1) TECO_PICK(0, 1, 2, 1)
   TECO_PICK(1, 3, 1, 1) TECO_PICK(1, 3, 2, 1) TECO_PICK(1, 1, 1, 1) TECO_PICK(1, 1, 2, 1)
+  TECO_PICK(2, 3, 2, 1) TECO_PICK(2, 3, 3, 1) TECO_PICK(2, 3, 4, 1)
 #undef TECO_PICK
   if (!kern) {
     teco_set_error("teco_conv3x3_tc: no kernel instantiation for mode=%d TPS=%d J=%d KS=%d", d->mode, p.TPS, J, p.KS);

@@ -102,7 +102,7 @@ __global__ void warp_bwd_f32_kernel(const float* __restrict__ img, const float* 
 // per-thread gather moved 30 sectors per request through L1, 31x the unique bytes).  Windows that do not fit
 // (|flow| spread > ~40 px inside one tile) take the direct global gather path.
 constexpr int WS_TLH = 2, WS_TLW = 32;                 // LR tile
-constexpr int WS_SMEM_FLOATS = 6 * 1024;               // 24 KB window budget: up to ~14 x 146 source pixels, 8 CTAs / SM
+constexpr int WS_SMEM_FLOATS = 8 * 1024;               // 32 KB window budget: up to ~16 x 168 source pixels, 7 CTAs / SM
 
 struct FlowQ { float2 f00, f01, f10, f11; };
 
@@ -121,44 +121,50 @@ __device__ __forceinline__ FlowQ load_flow_quad(const float* __restrict__ fb, in
   return q;
 }
 
+// One tile per CTA (grid = tiles_x x tiles_y x N: no index divisions), five CTAs per SM.  Phases: (1) the first four warps
+// bound the flow over the tile, (2) all threads issue 16-byte cp.async copies of the source window, (3) WHILE those are in
+// flight every thread interpolates its own flow and sets up its four bilinear queries, (4) gather + blend from the window.
+// Round-2 ncu of the first versions: 227 thread instructions per HR pixel at IPC 2.2 -- the kernel was instruction- and
+// latency-bound, not memory-bound: generic loads through a run-time selected pointer, 64-bit index arithmetic and integer
+// divisions.  This version keeps each address space in its own code path and all per-pixel index arithmetic in 32 bits.
 template <bool kBf16>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 5)
 warp_s2d_fused_kernel(const float* __restrict__ pre_gen, const float* __restrict__ flow_lr, void* __restrict__ dst,
                       float* __restrict__ warped_out, int N, int h, int w, int fh, int fw, int dst_cpitch, int ch_off,
-                      float in_scale, float in_shift, int tiles_x, int tiles_y) {
-  extern __shared__ float win[];
-  __shared__ float red[4][8];
-  __shared__ int s_win[5];   // y_lo, x_lo, rows, cols, use_smem
+                      float in_scale, float in_shift) {
+  extern __shared__ __align__(16) float win[];
+  __shared__ float red[4][4];
+  __shared__ int s_win[6];   // y_lo, x_lo, rows, cols, use_smem, interior (no query of the tile can touch a clamp)
   const int H = 4 * h, W = 4 * w;
-  int tile = blockIdx.x;
-  const int tx = tile % tiles_x; tile /= tiles_x;
-  const int ty = tile % tiles_y;
-  const int n = tile / tiles_y;
-  const int ly0 = ty * WS_TLH, lx0 = tx * WS_TLW;
-  const float* fb = flow_lr + (long long)n * fh * fw * 2;
-  const float* img = pre_gen + (long long)n * H * W * 3;
+  const int n = blockIdx.z, ly0 = blockIdx.y * WS_TLH, lx0 = blockIdx.x * WS_TLW;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float* fb = flow_lr + (size_t)n * fh * fw * 2;
+  const float* img = pre_gen + (size_t)n * H * W * 3;
 
-  // ---- bound the flow over the tile: samples (ly0..ly0+2) x (lx0..lx0+32), clamped like upscale_four
-  float mny = 1e30f, mxy = -1e30f, mnx = 1e30f, mxx = -1e30f;
-  if (tid < (WS_TLH + 1) * (WS_TLW + 1)) {
-    int i = min(ly0 + tid / (WS_TLW + 1), h - 1), j = min(lx0 + tid % (WS_TLW + 1), w - 1);
-    int si = i < fh ? i : 2 * fh - 1 - i, sj = j < fw ? j : 2 * fw - 1 - j;
-    float2 f = *reinterpret_cast<const float2*>(fb + ((long long)si * fw + sj) * 2);
-    mny = mxy = f.x * 4.f;
-    mnx = mxx = f.y * 4.f;
-  }
+  // ---- (1) bound the flow over the tile: samples (ly0..ly0+2) x (lx0..lx0+32), clamped like upscale_four
+  if (wid < 4) {
+    float mny = 1e30f, mxy = -1e30f, mnx = 1e30f, mxx = -1e30f;
+    if (tid < (WS_TLH + 1) * (WS_TLW + 1)) {
+      const int r = tid >= 2 * (WS_TLW + 1) ? 2 : (tid >= (WS_TLW + 1) ? 1 : 0);
+      const int i = min(ly0 + r, h - 1), j = min(lx0 + tid - r * (WS_TLW + 1), w - 1);
+      const int si = i < fh ? i : 2 * fh - 1 - i, sj = j < fw ? j : 2 * fw - 1 - j;
+      const float2 f = *reinterpret_cast<const float2*>(fb + (si * fw + sj) * 2);
+      mny = mxy = f.x * 4.f;
+      mnx = mxx = f.y * 4.f;
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    for (int o = 16; o > 0; o >>= 1) {
+      mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+      mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+      mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+      mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    }
+    if (lane == 0) { red[0][wid] = mny; red[1][wid] = mxy; red[2][wid] = mnx; red[3][wid] = mxx; }
   }
-  if (lane == 0) { red[0][wid] = mny; red[1][wid] = mxy; red[2][wid] = mnx; red[3][wid] = mxx; }
   __syncthreads();
   if (tid == 0) {
-    for (int k = 1; k < TPB / 32; ++k) {
+    float mny = red[0][0], mxy = red[1][0], mnx = red[2][0], mxx = red[3][0];
+    for (int k = 1; k < 4; ++k) {
       mny = fminf(mny, red[0][k]); mxy = fmaxf(mxy, red[1][k]);
       mnx = fminf(mnx, red[2][k]); mxx = fmaxf(mxx, red[3][k]);
     }
@@ -168,93 +174,149 @@ warp_s2d_fused_kernel(const float* __restrict__ pre_gen, const float* __restrict
     int y_hi = (int)fminf(fmaxf(floorf((float)(Y0 + 4 * WS_TLH - 1) - mny) + 1.f, 0.f), (float)(H - 2)) + 1;
     int x_lo = (int)fminf(fmaxf(floorf((float)X0 - mxx) - 1.f, 0.f), (float)(W - 2));
     int x_hi = (int)fminf(fmaxf(floorf((float)(X0 + 4 * WS_TLW - 1) - mnx) + 1.f, 0.f), (float)(W - 2)) + 1;
-    int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
+    // columns in whole groups of four pixels (48 bytes): every window row then starts and ends on a 16-byte boundary of
+    // the fp32 RGB image (W = 4w is a multiple of 4), so the window can be fetched with 16-byte asynchronous copies
+    x_lo &= ~3;
+    x_hi = min(x_hi | 3, W - 1);
+    const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
     s_win[0] = y_lo; s_win[1] = x_lo; s_win[2] = rows; s_win[3] = cols;
     // stage only when the window is compact (<= 2.5x the tile's own 8x128 pixels): rough flow fields would re-read more
     // through the window than the direct L1 gather does
-    s_win[4] = ((long long)rows * cols * 3 <= WS_SMEM_FLOATS && (long long)rows * cols * 2 <= 5LL * (4 * WS_TLH) * (4 * WS_TLW)) ? 1 : 0;
+    s_win[4] = (rows * cols * 3 <= WS_SMEM_FLOATS && rows * cols * 2 <= 5 * (4 * WS_TLH) * (4 * WS_TLW)) ? 1 : 0;
+    // every query of the tile lies at least one pixel inside [0, size-2]: floor needs no clamp and the fraction is in [0,1)
+    s_win[5] = ((float)Y0 - mxy >= 1.f && (float)(Y0 + 4 * WS_TLH - 1) - mny <= (float)(H - 3) &&
+                (float)X0 - mxx >= 1.f && (float)(X0 + 4 * WS_TLW - 1) - mnx <= (float)(W - 3)) ? 1 : 0;
   }
   __syncthreads();
-  const int y_lo = s_win[0], x_lo = s_win[1], rows = s_win[2], cols = s_win[3];
-  const bool use_smem = s_win[4] != 0;
-  const int rowf = cols * 3;
-  if (use_smem) {   // coalesced row copies of the window
+  const int y_lo = s_win[0], x_lo = s_win[1], rowf = s_win[3] * 3;
+  const bool use_smem = s_win[4] != 0, interior = s_win[5] != 0;
+
+  // ---- (2) the whole window in flight at once: 16-byte cp.async copies (no register staging); a warp per window row
+  if (use_smem) {
+    const int rows = s_win[2], cpr = rowf >> 2;       // 16-byte chunks per window row (rowf is a multiple of 12 floats)
+    const float* src0 = img + ((size_t)y_lo * W + x_lo) * 3;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(win);
     for (int r = wid; r < rows; r += TPB / 32) {
-      const float* src = img + ((long long)(y_lo + r) * W + x_lo) * 3;
-      float* d = win + r * rowf;
-      int k = lane;
-      for (; k + 96 < rowf; k += 128) {          // four independent 128-byte warp loads in flight
-        float a0 = src[k], a1 = src[k + 32], a2 = src[k + 64], a3 = src[k + 96];
-        d[k] = a0; d[k + 32] = a1; d[k + 64] = a2; d[k + 96] = a3;
+      const float* src = src0 + (size_t)r * (W * 3);
+      const uint32_t drow = sbase + (uint32_t)(r * rowf) * 4u;
+      for (int k = lane; k < cpr; k += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(drow + 16u * k), "l"(src + 4 * k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // ---- (3) this thread's four queries: HR column X = 4 lx + dx of the four HR sub-rows dy of one LR row.  A warp covers 32
+  // consecutive HR columns, so its window reads step by 3 floats from lane to lane (conflict-free; the (LR pixel, dy) mapping
+  // of round 1 hit 8 of 32 banks).  flow = upscale_four(4 * flow_lr) written as T + (B - T) * (dy/4) per component.
+  // floor / float->int by the 1.5*2^23 trick on the FMA pipe: ncu showed the XU pipe (FRND, F2I, I2F) 95 % busy.
+  const int xl = tid & (4 * WS_TLW - 1), lyl = tid >> 7;
+  const int dx = xl & 3, lx = lx0 + (xl >> 2), ly = ly0 + lyl;
+  const bool valid = ly < h && lx < w;
+  int off[4];
+  float ax[4], ay[4];
+  {
+    const int lyc = min(ly, h - 1), lxc = min(lx, w - 1);
+    const FlowQ q = load_flow_quad(fb, lyc, lxc, h, w, fh, fw);
+    const float wx1 = 0.25f * dx, wx0 = 1.f - wx1;
+    const float Ty = q.f00.x * wx0 + q.f01.x * wx1, Dy = (q.f10.x * wx0 + q.f11.x * wx1) - Ty;
+    const float Tx = q.f00.y * wx0 + q.f01.y * wx1, Dx = (q.f10.y * wx0 + q.f11.y * wx1) - Tx;
+    const float Yf = (float)(4 * lyc), Xf = (float)(4 * lxc + dx);
+    const int pitch = use_smem ? rowf : W * 3;
+    const int yo = use_smem ? y_lo : 0, xo = use_smem ? x_lo : 0;
+    const float hy = (float)(H - 2), hx = (float)(W - 2);
+    auto floor_fi = [](float v, float& f, int& i) {   // floor for |v| < 2^22 without FRND / F2I
+      const float t = v + 12582912.f;                 // 1.5 * 2^23: round to nearest integer
+      f = t - 12582912.f;
+      i = __float_as_int(t) - 0x4B400000;
+      if (f > v) { f -= 1.f; i -= 1; }
+    };
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+      const float qy = (Yf + (float)dy) - (Ty + Dy * (0.25f * dy)), qx = Xf - (Tx + Dx * (0.25f * dy));
+      float fy, fx;
+      int iy, ix;
+      floor_fi(qy, fy, iy);
+      floor_fi(qx, fx, ix);
+      if (interior) {                                 // CTA-uniform: 14 instructions per pixel less on all but border tiles
+        ay[dy] = qy - fy;
+        ax[dy] = qx - fx;
+      } else {
+        fy = fminf(fmaxf(fy, 0.f), hy);               // dense_image_warp: floor clamped to [0, size-2], fraction to [0,1]
+        fx = fminf(fmaxf(fx, 0.f), hx);
+        iy = min(max(iy, 0), H - 2);
+        ix = min(max(ix, 0), W - 2);
+        ay[dy] = fminf(fmaxf(qy - fy, 0.f), 1.f);
+        ax[dy] = fminf(fmaxf(qx - fx, 0.f), 1.f);
       }
-      for (; k < rowf; k += 32) d[k] = src[k];
+      off[dy] = (iy - yo) * pitch + (ix - xo) * 3;
     }
   }
+  if (use_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
-  const int dy = tid & 3, lxl = (tid >> 2) & (WS_TLW - 1), lyl = tid >> 7;
-  const int ly = ly0 + lyl, lx = lx0 + lxl;
-  if (ly >= h || lx >= w) return;
-  const FlowQ q = load_flow_quad(fb, ly, lx, h, w, fh, fw);
-  const float wy1 = 0.25f * dy, wy0 = 1.f - wy1;
-  const int Y = 4 * ly + dy;
-  float vals[12];
+  // ---- (4) gather + blend; each address space in its own code path
+  float vals[4][3];
+  auto gather = [&](const float* __restrict__ base, int pitch) {
 #pragma unroll
-  for (int dx = 0; dx < 4; ++dx) {
-    float wx1 = 0.25f * dx, wx0 = 1.f - wx1;
-    float fy = q.f00.x * wy0 * wx0 + q.f01.x * wy0 * wx1 + q.f10.x * wy1 * wx0 + q.f11.x * wy1 * wx1;
-    float fx = q.f00.y * wy0 * wx0 + q.f01.y * wy0 * wx1 + q.f10.y * wy1 * wx0 + q.f11.y * wy1 * wx1;
-    int X = 4 * lx + dx;
-    Bil b = bil_setup((float)Y - fy, (float)X - fx, H, W);
-    const float *p00, *p10;
-    if (use_smem) {
-      p00 = win + (b.y0 - y_lo) * rowf + (b.x0 - x_lo) * 3;
-      p10 = p00 + rowf;
-    } else {
-      p00 = img + ((long long)b.y0 * W + b.x0) * 3;
-      p10 = p00 + (long long)W * 3;
+    for (int dy = 0; dy < 4; ++dy) {
+      const float* p00 = base + off[dy];
+      const float* p10 = p00 + pitch;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float tl = p00[c], tr = p00[3 + c], bl = p10[c], br = p10[3 + c];
+        const float top = ax[dy] * (tr - tl) + tl;
+        const float bot = ax[dy] * (br - bl) + bl;
+        vals[dy][c] = ay[dy] * (bot - top) + top;
+      }
     }
+  };
+  if (use_smem) gather(win, rowf);
+  else gather(img, W * 3);
+
+  if (warped_out && valid) {
+    float* wo = warped_out + (((size_t)n * H + 4 * ly) * W + 4 * lx + dx) * 3;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float tl = p00[c], tr = p00[3 + c], bl = p10[c], br = p10[3 + c];
-      float top = b.ax * (tr - tl) + tl;
-      float bot = b.ax * (br - bl) + bl;
-      vals[dx * 3 + c] = b.ay * (bot - top) + top;
+    for (int dy = 0; dy < 4; ++dy) {
+      wo[(size_t)dy * W * 3 + 0] = vals[dy][0];
+      wo[(size_t)dy * W * 3 + 1] = vals[dy][1];
+      wo[(size_t)dy * W * 3 + 2] = vals[dy][2];
     }
   }
-  if (warped_out) {
-    float* wo = warped_out + (((long long)n * H + Y) * W + 4 * lx) * 3;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(wo + 4 * k) = make_float4(vals[4 * k], vals[4 * k + 1], vals[4 * k + 2], vals[4 * k + 3]);
-  }
-  long long o = (((long long)n * h + ly) * w + lx) * dst_cpitch + ch_off + dy * 12;
+  // space-to-depth: element (dy*4 + dx)*3 + c of the 48 channels of LR pixel (ly, lx)
+  const size_t o = (((size_t)n * h + min(ly, h - 1)) * w + min(lx, w - 1)) * dst_cpitch + ch_off;
   if (kBf16) {
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst) + o;
-    if ((o & 3) == 0) {
+    const bool vec = ((o & 3) == 0);                 // warp-uniform per LR row except through lx; all lanes shuffle anyway
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(vals[4 * k] * in_scale + in_shift, vals[4 * k + 1] * in_scale + in_shift);
-        __nv_bfloat162 c = __floats2bfloat162_rn(vals[4 * k + 2] * in_scale + in_shift, vals[4 * k + 3] * in_scale + in_shift);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&a);
-        u.y = *reinterpret_cast<uint32_t*>(&c);
-        *reinterpret_cast<uint2*>(d + 4 * k) = u;
+    for (int dy = 0; dy < 4; ++dy) {
+      const float v0 = vals[dy][0] * in_scale + in_shift, v1 = vals[dy][1] * in_scale + in_shift, v2 = vals[dy][2] * in_scale + in_shift;
+      // the 12 values of (LR pixel, dy) sit in four neighbouring lanes (dx = 0..3): lanes dx = 0,1,2 each write 8 bytes
+      const float n0 = __shfl_down_sync(0xffffffffu, v0, 1), n1 = __shfl_down_sync(0xffffffffu, v1, 1),
+                  n2 = __shfl_down_sync(0xffffffffu, v2, 1);
+      if (!valid) continue;
+      if (vec) {
+        if (dx < 3) {
+          const float e0 = dx == 0 ? v0 : (dx == 1 ? v1 : v2), e1 = dx == 0 ? v1 : (dx == 1 ? v2 : n0),
+                      e2 = dx == 0 ? v2 : (dx == 1 ? n0 : n1), e3 = dx == 0 ? n0 : (dx == 1 ? n1 : n2);
+          __nv_bfloat162 a = __floats2bfloat162_rn(e0, e1), c = __floats2bfloat162_rn(e2, e3);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&a);
+          u.y = *reinterpret_cast<uint32_t*>(&c);
+          *reinterpret_cast<uint2*>(d + dy * 12 + dx * 4) = u;
+        }
+      } else {
+        d[dy * 12 + dx * 3 + 0] = __float2bfloat16_rn(v0);
+        d[dy * 12 + dx * 3 + 1] = __float2bfloat16_rn(v1);
+        d[dy * 12 + dx * 3 + 2] = __float2bfloat16_rn(v2);
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) d[k] = __float2bfloat16_rn(vals[k] * in_scale + in_shift);
     }
-  } else {
+  } else if (valid) {
     float* d = reinterpret_cast<float*>(dst) + o;
-    if ((o & 3) == 0) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
-        *reinterpret_cast<float4*>(d + 4 * k) =
-            make_float4(vals[4 * k] * in_scale + in_shift, vals[4 * k + 1] * in_scale + in_shift,
-                        vals[4 * k + 2] * in_scale + in_shift, vals[4 * k + 3] * in_scale + in_shift);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) d[k] = vals[k] * in_scale + in_shift;
+    for (int dy = 0; dy < 4; ++dy) {
+      d[dy * 12 + dx * 3 + 0] = vals[dy][0] * in_scale + in_shift;
+      d[dy * 12 + dx * 3 + 1] = vals[dy][1] * in_scale + in_shift;
+      d[dy * 12 + dx * 3 + 2] = vals[dy][2] * in_scale + in_shift;
     }
   }
 }
@@ -601,8 +663,7 @@ int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, f
   TECO_CHECK_ARG(ch_off >= 0 && ch_off + 48 <= dst_cpitch, "teco_warp_s2d_fused: 48 channels do not fit at ch_off=%d in pitch %d",
                  ch_off, dst_cpitch);
   const int tiles_x = teco_ceil_div(w, WS_TLW), tiles_y = teco_ceil_div(h, WS_TLH);
-  const long long ctas = (long long)N * tiles_x * tiles_y;
-  TECO_CHECK_ARG(ctas < (1LL << 31), "teco_warp_s2d_fused: too many tiles");
+  TECO_CHECK_ARG(tiles_y <= 65535 && N <= 65535, "teco_warp_s2d_fused: more than 65535 row bands or images");
   const size_t smem = WS_SMEM_FLOATS * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -612,12 +673,14 @@ int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, f
   }
   // the 4-float stores of warped_out need 16-byte alignment of every (row, 4*lx) start: W*3 floats per row, 4*lx*3 = 12 lx
   TECO_CHECK_ARG(!warped_out || ((((uintptr_t)warped_out) & 15) == 0), "teco_warp_s2d_fused: warped_out must be 16-byte aligned");
+  TECO_CHECK_ARG((((uintptr_t)pre_gen) & 15) == 0, "teco_warp_s2d_fused: pre_gen must be 16-byte aligned");
+  const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)N);
   if (dst_bf16)
-    warp_s2d_fused_kernel<true><<<(unsigned)ctas, TPB, smem, (cudaStream_t)stream>>>(pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw,
-                                                                                 dst_cpitch, ch_off, in_scale, in_shift, tiles_x, tiles_y);
+    warp_s2d_fused_kernel<true><<<grid, TPB, smem, (cudaStream_t)stream>>>(pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw, dst_cpitch,
+                                                                          ch_off, in_scale, in_shift);
   else
-    warp_s2d_fused_kernel<false><<<(unsigned)ctas, TPB, smem, (cudaStream_t)stream>>>(pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw,
-                                                                                  dst_cpitch, ch_off, in_scale, in_shift, tiles_x, tiles_y);
+    warp_s2d_fused_kernel<false><<<grid, TPB, smem, (cudaStream_t)stream>>>(pre_gen, flow_lr, dst, warped_out, N, h, w, fh, fw, dst_cpitch,
+                                                                           ch_off, in_scale, in_shift);
   TECO_CUDA_LAUNCH_CHECK("teco_warp_s2d_fused");
   return TECO_OK;
 }

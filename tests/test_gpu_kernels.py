@@ -304,6 +304,26 @@ def test_conv3x3_tc_fp32_output_stage_streaming_from_hbm():
         assert_close(out[i:i + 1], ref, 1e-4, what="output stage image %d" % i)
 
 
+@pytest.mark.parametrize("n,h,w,c", [(3, 128, 128, 3), (2, 144, 180, 3), (1, 512, 512, 3), (40, 32, 32, 2), (7, 48, 22, 4)])
+def test_kx_fused_narrow_output_stage_matches_oracle(n, h, w, c):
+    """Many-tile fp32 output stages run the kx-fused kernel (one MMA per kernel row, shuffle-combined columns): every
+    width class (multiple of the tile width or not), with and without the bicubic residual."""
+    from tecogan_b200 import kernels as K
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(n, h, w, 64, generator=g).to(torch.bfloat16)
+    wt, b = _bf(rnd(2, 3, 3, 64, c) * 0.05), rnd(3, c) * 0.1
+    bic = torch.rand(n, h, w, c, generator=g)
+    wpk = K.packed_weight(dev(wt), 64, 16)
+    out = torch.zeros(n, h, w, c, device="cuda")
+    K.conv3x3_tc(x.cuda(), wpk, K.pad_bias(dev(b), 16), cout=16, out_f32=out, res_f32=bic.cuda(), post=(2.0, -1.0))
+    ref = (O.conv2d(x[:2].float(), wt, b) + bic[:2]) * 2 - 1
+    assert_close(out[:2], ref, 1e-4, what="kx-fused output stage")
+    out2 = torch.zeros(n, h, w, c, device="cuda")
+    K.conv3x3_tc(x.cuda(), wpk, K.pad_bias(dev(b), 16), cout=16, act=K.ACT_TANH24, out_f32=out2)
+    ref2 = torch.tanh(O.conv2d(x[-1:].float(), wt, b)) * 24.0
+    assert_close(out2[-1:], ref2, 2e-4, what="kx-fused tanh head")
+
+
 def test_abi_rejects_bad_arguments_with_valueerror():
     from tecogan_b200 import kernels as K
     with pytest.raises(ValueError):
