@@ -96,6 +96,17 @@ int64_t teco_packed_weight_bytes(int32_t cin_pad, int32_t cout_pad);
 int teco_conv3x3_tc(const teco_tc_desc* d, const void* x, const void* wpk, const float* bias,
                     const void* res, void* y, const float* res_f32, float* out_f32, void* stream);
 
+/* Bias gradient of conv2() (slim.conv2d biases, reference lib/ops.py:47-56): db[c] (+)= sum over npix pixels of dy[pixel*cpitch + c]. */
+int teco_bias_grad_f32(const float* dy, float* db, int64_t npix, int32_t C, int32_t cpitch, int32_t accumulate, void* stream);
+
+/* Weight gradient of conv2() 3x3 stride 1 SAME on tcgen05 (the gradient tf.train.AdamOptimizer.compute_gradients takes
+ * through slim.conv2d: reference lib/ops.py:47-56, lib/Teco.py:426,446-447):
+ *   dw[ky][kx][ci][co] (+)= sum_p x[p + (ky-1,kx-1)][ci] * dz[p][co],  dw fp32 in TF layout [3,3,cin,cout].
+ * x [N,H,W,cin_pad], dz [N,H,W,cout_pad]: NHWC bf16, channel counts padded to multiples of 64; cout % 4 == 0.
+ * accumulate == 0 zeroes dw first (pixel tiles are summed with fp32 atomics). */
+int teco_conv3x3_wgrad_tc(int32_t N, int32_t H, int32_t W, int32_t cin_pad, int32_t cout_pad, int32_t cin, int32_t cout,
+                          const void* x, const void* dz, float* dw, int32_t accumulate, void* stream);
+
 /* Fused generator trunk (reference lib/frvsr.py:59-70): input conv + N residual blocks = num_layers = 2N+1 layers of
  * 3x3 64->64 in ONE launch; tiles hand over to their neighbours through per-tile counters instead of kernel boundaries.
  * x_in / buf_a / buf_b: NHWC bf16 [N,H,W,64]; layer 0: x_in -> a (ReLU); odd l: a -> b (ReLU); even l >= 2: b -> a, + a.

@@ -42,6 +42,8 @@ SIGNATURES = {
     "teco_pack_conv3x3_bf16": [_P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P],
     "teco_packed_weight_bytes": [_I32, _I32],
     "teco_conv3x3_tc": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "teco_bias_grad_f32": [_P, _P, _I64, _I32, _I32, _I32, _P],
+    "teco_conv3x3_wgrad_tc": [_I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P],
     "teco_debug_timing": [_P],
     "teco_trunk64_supported": [_I32, _I32, _I32, _I32],
     "teco_trunk64_tc": [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P],

@@ -591,6 +591,23 @@ def _from_bf16_rows(yb, C, add=None):
     return y
 
 
+def conv3x3_wgrad_tc(xb, dzb, dw, cin, cout, accumulate=False):
+    """dw[3,3,cin,cout] fp32 (+)= sum_p xb[p+tap][ci] dzb[p][co] on tcgen05 (teco_conv3x3_wgrad_tc); xb / dzb: NHWC bf16 with
+    channel counts padded to multiples of 64."""
+    N, H, W, cp = xb.shape
+    call("teco_conv3x3_wgrad_tc", N, H, W, cp, dzb.shape[-1], cin, cout, ptr(xb, bf16), ptr(dzb, bf16), ptr(dw, f32),
+         int(accumulate), stream_ptr())
+    return dw
+
+
+def bias_grad(dz, C=None):
+    """db[c] = sum over pixels of dz[..., c] (fp32)."""
+    C = dz.shape[-1] if C is None else C
+    db = torch.empty(C, device=dz.device, dtype=f32)
+    call("teco_bias_grad_f32", ptr(dz, f32), ptr(db, f32), dz.numel() // dz.shape[-1], C, dz.shape[-1], 0, stream_ptr())
+    return db
+
+
 class _Conv3x3TC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, act, res):
@@ -600,33 +617,40 @@ class _Conv3x3TC(torch.autograd.Function):
         Cin, Cout = w.shape[2], w.shape[3]
         cip, cop = _pad64(Cin), _pad64(Cout)
         wpk, bp = _tc_packed(w, b, 0, cip, cop)
-        yb = conv3x3_tc(_to_bf16_rows(x, cip), wpk, bp, cout=cop, act=act)
+        xb = _to_bf16_rows(x, cip)
+        yb = conv3x3_tc(xb, wpk, bp, cout=cop, act=act)
         y = _from_bf16_rows(yb, Cout, None if res is None else _cc(res))
         ctx.cfg = (act, b is not None, res is not None)
-        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        # the bf16 copy of x feeds the tensor-core weight gradient (half the bytes of the fp32 activation)
+        ctx.save_for_backward(xb if ctx.needs_input_grad[1] else None, w, y if act != ACT_NONE else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         act, has_b, has_res = ctx.cfg
-        x, w, y = ctx.saved_tensors
+        xb, w, y = ctx.saved_tensors
         dy = _cc(dy)
         dz = dy
         if act != ACT_NONE:
             dz = torch.empty_like(dy)
             call("teco_act_bwd_f32", ptr(y, f32), ptr(dy, f32), ptr(dz, f32), dy.numel(), act, stream_ptr())
-        N, H, W, Cin = x.shape
-        Cout = w.shape[3]
+        Cin, Cout = w.shape[2], w.shape[3]
         cip, cop = _pad64(Cin), _pad64(Cout)
         dx = dw = db = None
+        dzb = _to_bf16_rows(dz, cop)
         if ctx.needs_input_grad[0]:
             wpk_t, _ = _tc_packed(w, None, 3, cop, cip)          # flipped taps, Cin <-> Cout
-            dxb = conv3x3_tc(_to_bf16_rows(dz, cop), wpk_t, None, cout=cip, act=ACT_NONE)
+            dxb = conv3x3_tc(dzb, wpk_t, None, cout=cip, act=ACT_NONE)
             dx = _from_bf16_rows(dxb, Cin)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            db = torch.empty(Cout, device=x.device, dtype=f32) if has_b and ctx.needs_input_grad[2] else None
-            conv2d_wgrad_raw(x, dz, dw, db, stride=1, pad_t=1, pad_l=1, OH=H, OW=W)
+            if Cout % 4 == 0:
+                conv3x3_wgrad_tc(xb, dzb, dw, Cin, Cout)          # tcgen05, pixels as the contraction dimension
+            else:   # 16-byte atomics need Cout % 4 == 0: fp32 kernel on the widened bf16 activation
+                N, H, W, _ = xb.shape
+                conv2d_wgrad_raw(bf16_to_f32(xb, Cin), dz, dw, None, stride=1, pad_t=1, pad_l=1, OH=H, OW=W)
+            if has_b and ctx.needs_input_grad[2]:
+                db = bias_grad(dz)
         return dx, dw, db, None, (dy if has_res else None)
 
 

@@ -324,6 +324,26 @@ def test_kx_fused_narrow_output_stage_matches_oracle(n, h, w, c):
     assert_close(out2[-1:], ref2, 2e-4, what="kx-fused tanh head")
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 16, 64, 64), (4, 32, 32, 64, 64), (2, 19, 21, 51, 64), (3, 16, 24, 128, 32), (2, 32, 32, 32, 256)])
+def test_conv3x3_wgrad_tc_matches_autograd_on_bf16_operands(n, h, w, cin, cout):
+    """tcgen05 weight gradient (pixels as the GEMM K dimension, MN-major operands, two taps per MMA) against torch autograd
+    of the oracle convolution on the same bf16-rounded x and dz; ragged sizes exercise the zero-filled tile edges."""
+    from tecogan_b200 import kernels as K
+    x, dz = _bf(rnd(1, n, h, w, cin)), _bf(rnd(2, n, h, w, cout))
+    wt = torch.zeros(3, 3, cin, cout, requires_grad=True)
+    (O.conv2d(x, wt, None) * dz).sum().backward()
+    ref = wt.grad
+    dw = torch.full((3, 3, cin, cout), 7.0, device="cuda")
+    K.conv3x3_wgrad_tc(_xpad(x), _xpad(dz), dw, cin, cout)
+    scale = ref.abs().max().item()
+    per_tap = [round((dw.cpu()[t // 3, t % 3] - ref[t // 3, t % 3]).abs().max().item() / scale, 4) for t in range(9)]
+    assert max(per_tap) < 2e-3, per_tap
+    K.conv3x3_wgrad_tc(_xpad(x), _xpad(dz), dw, cin, cout, accumulate=True)
+    assert (dw.cpu() - 2 * ref).abs().max().item() < 4e-3 * scale
+    db = K.bias_grad(dev(dz))
+    assert (db.cpu() - dz.sum(dim=(0, 1, 2))).abs().max().item() < 1e-3 * dz.abs().sum().item() ** 0.5
+
+
 def test_abi_rejects_bad_arguments_with_valueerror():
     from tecogan_b200 import kernels as K
     with pytest.raises(ValueError):
