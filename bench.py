@@ -357,9 +357,9 @@ def main():
     # the e2e leg really moved the bytes: spot-check the host copy against the device result of the last batch
     assert torch.equal(host_out[(args.steps - 1) & 1][-1, 0], eng.clip_u8[-1, 0].cpu()), "e2e: host frames differ from device frames"
 
-    # --- dominant kernel: the 3x3 64->64 res-block layer on the whole clip batch [B,32,32,64], timed alone (graph replay)
+    # --- dominant kernel: the generator trunk (input conv + 16 residual blocks = 33 layers of 3x3 64->64) on the whole clip
+    # batch [B,32,32,64] -- ONE launch of conv3x3_lin_kernel (kx-fused N=192 MMAs, CTA-local clips) -- timed alone (graph replay).
     g = eng.gen
-    c1, c2 = g.l_res[0]
     reps = 16
 
     def trunk_pairs(gp, n):
@@ -368,16 +368,28 @@ def main():
             K.conv3x3_tc(gp.a, a1.wpk, a1.bias, gp.b, cout=64, act=1)
             K.conv3x3_tc(gp.b, a2.wpk, a2.bias, gp.a, cout=64, act=0, res=gp.a)
 
-    def kernel_us(gp, n):
-        trunk_pairs(gp, n)
+    def graph_us(fn, n_inside, replays=5):
+        fn()
         torch.cuda.synchronize()
         kg = torch.cuda.CUDAGraph()          # graph replay: device time of the launches, not ctypes/Python overhead
         with torch.cuda.graph(kg):
-            trunk_pairs(gp, n)
+            fn()
         kg.replay()
-        return ev_time(lambda: [kg.replay() for _ in range(5)]) * 1000.0 / (5 * n)
-    k_us = kernel_us(g, reps)
-    k_flop = 2.0 * B * LR * LR * 576 * 64
+        return ev_time(lambda: [kg.replay() for _ in range(replays)]) * 1000.0 / (replays * n_inside)
+
+    def kernel_us(gp, n):
+        return graph_us(lambda: trunk_pairs(gp, n), n)
+    layer_flop = 2.0 * B * LR * LR * 576 * 64
+    per_layer_us = kernel_us(g, reps)                     # the per-layer persistent kernel (N = 64 MMAs), for comparison
+    if getattr(g, "lin", False):
+        n_layers = len(g.trunk_plan)
+        k_us = graph_us(lambda: [K.conv3x3_lin_chain(g.x_in, g.a, g.b, g.trunk_w, g.trunk_b, g.trunk_plan) for _ in range(2)], 2)
+        k_flop = layer_flop * n_layers
+        k_name = ("conv3x3_lin_kernel (generator trunk: %d layers of 3x3 64->64 on the clip batch [%d,32,32,64] in one launch; "
+                  "kx-fused N=192 tcgen05.mma, x-shift by warp shuffles)" % (n_layers, B))
+    else:
+        k_us, k_flop = per_layer_us, layer_flop
+        k_name = "conv3x3_tc_kernel (3x3 64->64 res-block layer on the clip batch [%d,32,32,64])" % B
 
     # --- HBM-bound kernel of the path: fused upscale_four + warp + space-to-depth feedback on a batch larger than L2
     # (32 clips of 256x256 LR -> 1024x1024 HR: 403 MB read + 201 MB written), algorithmic 18.5 B per HR pixel
@@ -415,10 +427,12 @@ def main():
                 "api": "tecogan_b200.engine.ClipEngine, pinned host clips in, pinned host uint8 frames out, copies on "
                        "separate streams overlapping the next batch"},
         "gpu_launches": int(launches_per_step * args.steps),
-        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (3x3 64->64 res-block layer on the clip batch [%d,32,32,64])" % B,
+        "roofline": {"bound": "tensor", "kernel": k_name,
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                      "peak_source": peak_src + ", burst bf16 (kernel timed alone)", "us_per_launch": k_us,
-                     "flop_per_launch": k_flop, "traffic": _traffic("r02_conv_tc_traffic.json"),
+                     "flop_per_launch": k_flop, "traffic": _traffic("r02_conv_lin_traffic.json"),
+                     "per_layer_kernel": {"kernel": "conv3x3_tc_kernel (same layers, one launch each, N=64 MMAs)", "us_per_layer": per_layer_us,
+                                          "achieved": layer_flop / (per_layer_us * 1e-6) / 1e12, "frac": layer_flop / (per_layer_us * 1e-6) / 1e12 / peak_tf},
                      "whole_step": {"algorithmic_gflop_per_clip": clip_flop() / 1e9, "achieved_tflops": whole_tf,
                                     "frac_of_sustained": whole_tf / peak_tf_sus}},
         "roofline_hbm": {"bound": "hbm", "kernel": "warp_s2d_fused_kernel (upscale_four + dense_image_warp + space_to_depth), "

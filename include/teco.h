@@ -116,6 +116,19 @@ int teco_trunk64_supported(int32_t N, int32_t H, int32_t W, int32_t num_layers);
 int teco_trunk64_tc(int32_t N, int32_t H, int32_t W, int32_t num_layers, const void* x_in, void* buf_a, void* buf_b,
                     const void* wpk_all, const float* bias_all, void* flags, void* stream);
 
+/* Row-linearised multi-layer 3x3 64->64 chain for 32-pixel-wide images (the metric configuration's 32x32 LR clips): the same
+ * layers of generator_F as teco_trunk64_tc (reference lib/frvsr.py:59-70) -- or any chain of conv2(3x3, 64->64) + bias + ReLU /
+ * LeakyReLU / none + optional residual -- in ONE launch.  One tcgen05.mma covers the three horizontal taps of a kernel row
+ * (N = 192, runs at the tensor floor; N = 64 cannot), the epilogue recombines them with warp shuffles; every CTA keeps its own
+ * images for all layers, so there is no grid-wide dependency between layers.
+ * x_in / buf_a / buf_b: NHWC bf16 [N,H,32,64] (buffer ids 0 / 1 / 2; x_in is never written).
+ * plan_host: HOST array [num_layers][4] = {input buffer id, output buffer id, residual buffer id or -1, TECO_ACT_*}.
+ *   A residual may be added in place (residual id == output id) but may not be the previous layer's output.
+ * wpk_all: num_layers packed layers back to back (teco_pack_conv3x3_bf16, 64x64 -> 73728 bytes each); bias_all [num_layers][64]. */
+int teco_conv3x3_lin_supported(int32_t N, int32_t H, int32_t W, int32_t num_layers);
+int teco_conv3x3_lin_tc(int32_t N, int32_t H, int32_t W, int32_t num_layers, const void* x_in, void* buf_a, void* buf_b,
+                        const void* wpk_all, const float* bias_all, const int32_t* plan_host, void* stream);
+
 /* Developer hook: when buf != NULL every teco_conv3x3_tc CTA writes clock64() stamps to buf[cta*32 ..] (phase
  * boundaries: start, setup done, halo landed, first/last weight slab landed, MMAs issued, accumulator ready,
  * epilogue done, teardown).  buf must hold gridDim*32 int64.  Pass NULL to switch it off. */

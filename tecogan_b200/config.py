@@ -1,5 +1,6 @@
 """Run-time configuration of the compute path (not part of the reference interface)."""
-_cfg = {"precision": "bf16", "train_precision": "fp32", "fused_trunk": __import__("os").environ.get("TECO_FUSED_TRUNK", "0") == "1"}
+_cfg = {"precision": "bf16", "train_precision": "fp32", "fused_trunk": __import__("os").environ.get("TECO_FUSED_TRUNK", "0") == "1",
+        "lin_trunk": __import__("os").environ.get("TECO_LIN_TRUNK", "1") == "1"}
 
 
 def set_precision(p):
@@ -38,3 +39,14 @@ def set_fused_trunk(on):
 
 def fused_trunk():
     return _cfg["fused_trunk"]
+
+
+def set_lin_trunk(on):
+    """32-pixel-wide frames (the metric configuration's 32x32 LR clips): run the generator's input conv + all residual
+    blocks as ONE launch of the row-linearised kx-fused kernel (teco_conv3x3_lin_tc; N = 192 MMAs at the tensor floor, every
+    CTA keeps its own clips for all layers).  On by default for batches of at least 8 clips; off -> one launch per layer."""
+    _cfg["lin_trunk"] = bool(on)
+
+
+def lin_trunk():
+    return _cfg["lin_trunk"]

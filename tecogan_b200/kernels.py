@@ -511,6 +511,25 @@ def conv3x3_tc(x, wpk, bias, y=None, *, cout, act=ACT_NONE, res=None, mode=0, ou
     return y if out_f32 is None else out_f32
 
 
+def conv3x3_lin_supported(N, H, W, num_layers):
+    from ._ffi import lib
+    return bool(lib().teco_conv3x3_lin_supported(N, H, W, num_layers))
+
+
+def conv3x3_lin_chain(x_in, buf_a, buf_b, wpk_all, bias_all, plan):
+    """A chain of 3x3 64->64 layers on 32-pixel-wide images in one launch (teco_conv3x3_lin_tc).  x_in / buf_a / buf_b:
+    [N,H,32,64] bf16 (buffer ids 0 / 1 / 2); plan: list of (input id, output id, residual id or -1, activation) per layer;
+    wpk_all: the packed layers back to back; bias_all: [L,64] fp32."""
+    import ctypes
+    N, H, W, C = x_in.shape
+    if C != 64:
+        raise ValueError("conv3x3_lin_chain: 64-channel NHWC bf16 tensors only (got %d channels)" % C)
+    L = len(plan)
+    flat = (ctypes.c_int32 * (4 * L))(*[int(v) for row in plan for v in row])
+    call("teco_conv3x3_lin_tc", N, H, W, L, ptr(x_in, bf16), ptr(buf_a, bf16), ptr(buf_b, bf16), ptr(wpk_all, bf16),
+         ptr(bias_all, f32), ctypes.cast(flat, ctypes.c_void_p), stream_ptr())
+
+
 def f32_to_bf16_pad(src, dst, C, c_off=0, scale=1.0, shift=0.0):
     npix = src.numel() // src.shape[-1]
     call("teco_f32_to_bf16_pad", ptr(src, f32), ptr(dst, bf16), npix, C, src.shape[-1], dst.shape[-1], c_off, float(scale),

@@ -135,6 +135,15 @@ class GeneratorPlan:
             self.trunk_b = torch.cat([l.bias for l in layers]).contiguous()
             self.trunk_flags = torch.zeros(B * ((h + 15) // 16) * ((w + 7) // 8), device=device, dtype=torch.int32)
             self.launches = 1 + 4 + 1
+        # 32-pixel-wide frames in a batch: the whole trunk as one launch of the row-linearised kx-fused kernel
+        self.lin = (not self.fused) and config.lin_trunk() and B >= 8 and K.conv3x3_lin_supported(B, h, w, 2 * num_resblock + 1)
+        if self.lin:
+            layers = [self.l_in] + [l for pair in self.l_res for l in pair]
+            self.trunk_w = torch.cat([l.wpk for l in layers]).contiguous()
+            self.trunk_b = torch.cat([l.bias for l in layers]).contiguous()
+            # buffer ids: 0 = x_in, 1 = a, 2 = b.  input conv x_in -> a (ReLU); block: a -> b (ReLU), b -> a (+ a)
+            self.trunk_plan = [(0, 1, -1, ACT_RELU)] + [(1, 2, -1, ACT_RELU), (2, 1, 1, ACT_NONE)] * num_resblock
+            self.launches = 1 + 4 + 1
 
     def run_bicubic(self, lr_f32, lr_cpitch=3):
         """bicubic_four(LR) for the output stage (lib/frvsr.py:84-86); independent of everything but the LR frame."""
@@ -149,6 +158,8 @@ class GeneratorPlan:
         if self.fused:
             call("teco_trunk64_tc", B, h, w, 2 * self.nrb + 1, ptr(self.x_in, bf16), ptr(self.a, bf16), ptr(self.b, bf16),
                  ptr(self.trunk_w, bf16), ptr(self.trunk_b, f32), ptr(self.trunk_flags), stream_ptr())
+        elif self.lin:
+            K.conv3x3_lin_chain(self.x_in, self.a, self.b, self.trunk_w, self.trunk_b, self.trunk_plan)
         else:
             K.conv3x3_tc(self.x_in, self.l_in.wpk, self.l_in.bias, self.a, cout=64, act=ACT_RELU)
             for c1, c2 in self.l_res:

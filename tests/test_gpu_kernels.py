@@ -264,6 +264,54 @@ def test_conv3x3_tc_matches_oracle_on_bf16_operands(n, h, w, cin, cout, act):
     assert_close(got, O.conv2d(x, wt, b) + res, 2e-3, 1.0 / 128, what="conv3x3_tc+res")
 
 
+def _lin_chain_reference(x, layers, plan):
+    """The chain in the oracle, with the kernel's rounding points: bf16 activations between layers, fp32 inside a layer."""
+    bufs = {0: x}
+    for (wt, b), (i, o, r, act) in zip(layers, plan):
+        y = O.conv2d(bufs[i], wt, b)
+        y = torch.relu(y) if act == 1 else (O.lrelu(y) if act == 2 else y)
+        if r >= 0:
+            y = y + bufs[r]
+        bufs[o] = _bf(y)
+    return bufs
+
+
+@pytest.mark.parametrize("n,h,plan", [
+    (1, 4, [(0, 1, -1, 1)]),                                               # one strip: every row is top and bottom padding
+    (3, 32, [(0, 1, -1, 0)]),
+    (5, 8, [(0, 1, 2, 2)]),                                                # external residual from buf_b, LeakyReLU
+    (2, 32, [(0, 1, -1, 1), (1, 2, -1, 1), (2, 1, 1, 0)]),                  # input conv + one residual block (in-place residual)
+    (150, 32, [(0, 1, -1, 1), (1, 2, -1, 1), (2, 1, 1, 0), (1, 2, -1, 1), (2, 1, 1, 0)]),   # > 148 images: CTAs with 1 and 2 images
+    (7, 12, [(0, 1, -1, 1)] + [(1, 2, -1, 1), (2, 1, 1, 0)] * 4),            # 9 layers: weight double buffer wraps
+])
+def test_conv3x3_lin_chain_matches_oracle_on_bf16_operands(n, h, plan):
+    """teco_conv3x3_lin_tc: kx-fused N=192 MMAs on row-linearised 32-pixel-wide images, multi-layer in one launch."""
+    from tecogan_b200 import kernels as K
+    L = len(plan)
+    x = _bf(rnd(1, n, h, 32, 64))
+    ext = _bf(rnd(5, n, h, 32, 64))                                         # initial content of buf_b (external residual case)
+    layers = [(_bf(rnd(10 + l, 3, 3, 64, 64) * (1.5 / 24.0)), rnd(50 + l, 64) * 0.1) for l in range(L)]
+    ref = _lin_chain_reference(x, layers, plan) if plan[0][2] < 0 else None
+    if ref is None:                                                          # single layer with the external residual
+        (wt, b), (_, _, _, act) = layers[0], plan[0]
+        ref = {1: _bf(O.lrelu(O.conv2d(x, wt, b)) + ext)}
+    assert K.conv3x3_lin_supported(n, h, 32, L) and not K.conv3x3_lin_supported(n, h, 40, L) and not K.conv3x3_lin_supported(n, 6, 32, L)
+    wall = torch.cat([K.packed_weight(dev(wt), 64, 64) for wt, _ in layers]).contiguous()
+    ball = torch.cat([dev(b) for _, b in layers]).contiguous()
+    a = torch.zeros(n, h, 32, 64, device="cuda", dtype=torch.bfloat16)
+    bb = dev(ext).to(torch.bfloat16)
+    K.conv3x3_lin_chain(dev(x).to(torch.bfloat16), a, bb, wall, ball, plan)
+    torch.cuda.synchronize()
+    final = plan[-1][1]
+    got = a if final == 1 else bb
+    # chained layers: each adds ~1 bf16 ulp of rounding noise that the next layers spread
+    assert_close(got, ref[final], 2e-3 * L, 1.0 / 128 * (1 + 0.5 * (L - 1)), what="conv3x3_lin chain (%d layers)" % L)
+    if L == 1:
+        # a single layer is the same arithmetic as teco_conv3x3_tc up to the fp32 summation order
+        other = K.conv3x3_tc(dev(x).to(torch.bfloat16), wall, ball, cout=64, act=plan[0][3], res=dev(ext).to(torch.bfloat16) if plan[0][2] >= 0 else None)
+        assert (got.float() - other.float()).abs().max().item() <= 2.0 ** -6 * max(1.0, got.float().abs().max().item())
+
+
 @pytest.mark.parametrize("n,h,w", [(1, 16, 8), (1, 32, 32), (2, 24, 20), (1, 64, 64), (5, 128, 128), (40, 64, 64), (3, 144, 120)])
 def test_conv_transpose_tc_matches_oracle_on_bf16_operands(n, h, w):
     from tecogan_b200 import kernels as K

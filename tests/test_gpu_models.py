@@ -240,16 +240,19 @@ def _y_psnr_delta(frames_lr, ours01, ref01):
     return max(d)
 
 
-def test_metric_config_clip_engine_matches_oracle_and_streaming_engine():
-    """bench.py headline path: B clips x 10 frames 32x32 in lock-step, one CUDA graph, fnet for all pairs first."""
+@pytest.mark.parametrize("B", [6, 12])
+def test_metric_config_clip_engine_matches_oracle_and_streaming_engine(B):
+    """bench.py headline path: B clips x 10 frames 32x32 in lock-step, one CUDA graph, fnet for all pairs first.
+    B = 12 takes the one-launch row-linearised trunk (teco_conv3x3_lin_tc, batches of >= 8 clips), B = 6 one launch per layer."""
     from tecogan_b200 import config
     from tecogan_b200.engine import ClipEngine, InferenceEngine
-    T, B, N = 10, 6, 16
+    T, N = 10, 16
     pg, pf = O.damp_generator(O.init_generator(seed=1234, num_resblock=N)), O.init_fnet(seed=4321)
     clips = _smooth_clips(T, B, 32, 32, seed=3)
     _fresh_store({**pg, **pf})
     config.set_precision("bf16")
     eng = ClipEngine(32, 32, T, N, batch=B)
+    assert eng.gen.lin == (B >= 8)
     u8 = eng.run(clips.cuda()).clone()
     u8_again = eng.run(clips.cuda()).clone()            # second replay of the captured graph: same bits
     assert torch.equal(u8, u8_again)
@@ -269,6 +272,17 @@ def test_metric_config_clip_engine_matches_oracle_and_streaming_engine():
         worst_dy = max(worst_dy, _y_psnr_delta([clips[t, b] for t in range(T)], ours, ref))
     assert worst_psnr > 40.0, worst_psnr
     assert worst_dy < 0.05, worst_dy
+    if B >= 8:
+        # the per-layer kernels on the same clips: same arithmetic up to the fp32 summation order inside a layer
+        config.set_lin_trunk(False)
+        try:
+            per_layer = ClipEngine(32, 32, T, N, batch=B)
+            assert not per_layer.gen.lin
+            u8_pl = per_layer.run(clips.cuda())
+        finally:
+            config.set_lin_trunk(True)
+        diff = (u8.float() - u8_pl.float()).abs()
+        assert diff.max().item() <= 3 and diff.mean().item() < 0.05, (diff.max().item(), diff.mean().item())
 
 
 def test_configs1_128x128_lookahead_graph_32_frames_matches_oracle():
