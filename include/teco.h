@@ -107,17 +107,8 @@ int teco_bias_grad_f32(const float* dy, float* db, int64_t npix, int32_t C, int3
 int teco_conv3x3_wgrad_tc(int32_t N, int32_t H, int32_t W, int32_t cin_pad, int32_t cout_pad, int32_t cin, int32_t cout,
                           const void* x, const void* dz, float* dw, int32_t accumulate, void* stream);
 
-/* Fused generator trunk (reference lib/frvsr.py:59-70): input conv + N residual blocks = num_layers = 2N+1 layers of
- * 3x3 64->64 in ONE launch; tiles hand over to their neighbours through per-tile counters instead of kernel boundaries.
- * x_in / buf_a / buf_b: NHWC bf16 [N,H,W,64]; layer 0: x_in -> a (ReLU); odd l: a -> b (ReLU); even l >= 2: b -> a, + a.
- * wpk_all: num_layers packed layers back to back (teco_pack_conv3x3_bf16, 64x64); bias_all: [num_layers][64] fp32;
- * flags: num_tiles uint32 scratch.  Only shapes with tiles(16x8) <= SM count (teco_trunk64_supported) -- the result is in buf_a. */
-int teco_trunk64_supported(int32_t N, int32_t H, int32_t W, int32_t num_layers);
-int teco_trunk64_tc(int32_t N, int32_t H, int32_t W, int32_t num_layers, const void* x_in, void* buf_a, void* buf_b,
-                    const void* wpk_all, const float* bias_all, void* flags, void* stream);
-
 /* Row-linearised multi-layer 3x3 64->64 chain for 32-pixel-wide images (the metric configuration's 32x32 LR clips): the same
- * layers of generator_F as teco_trunk64_tc (reference lib/frvsr.py:59-70) -- or any chain of conv2(3x3, 64->64) + bias + ReLU /
+ * layers of generator_F (input conv + residual blocks, reference lib/frvsr.py:59-70) -- or any chain of conv2(3x3, 64->64) + bias + ReLU /
  * LeakyReLU / none + optional residual -- in ONE launch.  One tcgen05.mma covers the three horizontal taps of a kernel row
  * (N = 192, runs at the tensor floor; N = 64 cannot), the epilogue recombines them with warp shuffles; every CTA keeps its own
  * images for all layers, so there is no grid-wide dependency between layers.

@@ -45,8 +45,6 @@ SIGNATURES = {
     "teco_bias_grad_f32": [_P, _P, _I64, _I32, _I32, _I32, _P],
     "teco_conv3x3_wgrad_tc": [_I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P],
     "teco_debug_timing": [_P],
-    "teco_trunk64_supported": [_I32, _I32, _I32, _I32],
-    "teco_trunk64_tc": [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P],
     "teco_conv3x3_lin_supported": [_I32, _I32, _I32, _I32],
     "teco_conv3x3_lin_tc": [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P],
     "teco_warp_f32": [_P, _P, _P, _I32, _I32, _I32, _I32, _P],

@@ -1,6 +1,5 @@
 """Run-time configuration of the compute path (not part of the reference interface)."""
-_cfg = {"precision": "bf16", "train_precision": "fp32", "fused_trunk": __import__("os").environ.get("TECO_FUSED_TRUNK", "0") == "1",
-        "lin_trunk": __import__("os").environ.get("TECO_LIN_TRUNK", "1") == "1"}
+_cfg = {"precision": "bf16", "train_precision": "fp32", "lin_trunk": __import__("os").environ.get("TECO_LIN_TRUNK", "1") == "1"}
 
 
 def set_precision(p):
@@ -28,17 +27,6 @@ def set_train_precision(p):
 
 def train_precision():
     return _cfg["train_precision"]
-
-
-def set_fused_trunk(on):
-    """Use the one-launch fused generator trunk (teco_trunk64_tc) when the frame is a single wave of tiles.
-    Off by default: bit-identical to the per-layer path but measured 252 us vs 215 us for the 33-layer 128x128 trunk
-    (profiles/conv_tc_r01_notes.md: the neighbour hand-shake runs at the pace of the slowest of nine tiles)."""
-    _cfg["fused_trunk"] = bool(on)
-
-
-def fused_trunk():
-    return _cfg["fused_trunk"]
 
 
 def set_lin_trunk(on):

@@ -126,17 +126,8 @@ class GeneratorPlan:
         self.bic = torch.zeros((B, 4 * h, 4 * w, 3), device=device, dtype=f32)
         self.out = torch.zeros((B, 4 * h, 4 * w, 3), device=device, dtype=f32)
         self.launches = 2 * num_resblock + 5 + 1
-        # fused trunk (input conv + all residual blocks in one launch) when the frame is a single wave of 16x8 tiles
-        from ._ffi import lib
-        self.fused = bool(lib().teco_trunk64_supported(B, h, w, 2 * num_resblock + 1)) and config.fused_trunk()
-        if self.fused:
-            layers = [self.l_in] + [l for pair in self.l_res for l in pair]
-            self.trunk_w = torch.cat([l.wpk for l in layers]).contiguous()
-            self.trunk_b = torch.cat([l.bias for l in layers]).contiguous()
-            self.trunk_flags = torch.zeros(B * ((h + 15) // 16) * ((w + 7) // 8), device=device, dtype=torch.int32)
-            self.launches = 1 + 4 + 1
         # 32-pixel-wide frames in a batch: the whole trunk as one launch of the row-linearised kx-fused kernel
-        self.lin = (not self.fused) and config.lin_trunk() and B >= 8 and K.conv3x3_lin_supported(B, h, w, 2 * num_resblock + 1)
+        self.lin = config.lin_trunk() and B >= 8 and K.conv3x3_lin_supported(B, h, w, 2 * num_resblock + 1)
         if self.lin:
             layers = [self.l_in] + [l for pair in self.l_res for l in pair]
             self.trunk_w = torch.cat([l.wpk for l in layers]).contiguous()
@@ -155,10 +146,7 @@ class GeneratorPlan:
         B, h, w = self.B, self.h, self.w
         if bicubic:
             self.run_bicubic(lr_f32, lr_cpitch)
-        if self.fused:
-            call("teco_trunk64_tc", B, h, w, 2 * self.nrb + 1, ptr(self.x_in, bf16), ptr(self.a, bf16), ptr(self.b, bf16),
-                 ptr(self.trunk_w, bf16), ptr(self.trunk_b, f32), ptr(self.trunk_flags), stream_ptr())
-        elif self.lin:
+        if self.lin:
             K.conv3x3_lin_chain(self.x_in, self.a, self.b, self.trunk_w, self.trunk_b, self.trunk_plan)
         else:
             K.conv3x3_tc(self.x_in, self.l_in.wpk, self.l_in.bias, self.a, cout=64, act=ACT_RELU)

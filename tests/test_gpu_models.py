@@ -169,34 +169,6 @@ def test_batched_clips_are_independent():
         assert torch.equal(a[1], b[0])
 
 
-@pytest.mark.parametrize("B,h,w,n", [(1, 32, 32, 3), (1, 128, 128, 16), (2, 48, 40, 4), (1, 144, 64, 2)])
-def test_fused_trunk_is_bit_identical_to_per_layer_launches(B, h, w, n):
-    """teco_trunk64_tc (input conv + all residual blocks in one launch, neighbour hand-shake through global counters)
-    against the same layers launched one by one -- same arithmetic order, so the outputs must be equal bit for bit;
-    repeated to shake out ordering races."""
-    from tecogan_b200 import config
-    from tecogan_b200.lib.frvsr import generator_F
-    from tecogan_b200.variables import variable_scope
-    p = O.damp_generator(O.init_generator(seed=21, num_resblock=n, bias_std=0.05))
-    g = torch.Generator().manual_seed(9)
-    x = torch.rand(B, h, w, 51, generator=g).cuda()
-    config.set_precision("bf16")
-    outs = {}
-    for fused in (False, True):
-        _fresh_store(p)
-        config.set_fused_trunk(fused)
-        try:
-            with torch.no_grad(), variable_scope('generator'):
-                outs[fused] = [generator_F(x, 3, reuse=False, FLAGS=Flags(num_resblock=n)).clone() for _ in range(5 if fused else 1)]
-        finally:
-            config.set_fused_trunk(False)
-    torch.cuda.synchronize()
-    for o in outs[True]:
-        assert torch.equal(o, outs[False][0])
-    ref = O.generator_F(p, x.cpu(), n)
-    assert O.psnr(outs[True][0].cpu().numpy(), ref.numpy(), peak=2.0) > 45.0
-
-
 def test_fnet_lookahead_is_bit_identical_to_the_serial_recurrence():
     """fnet(LR_i ++ LR_{i+1}) depends on no HR output (reference main.py:211), so the engine may run it concurrently with
     generator_F of frame i; every mix of look-ahead / serial steps must reproduce the serial outputs bit for bit."""

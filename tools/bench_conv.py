@@ -86,53 +86,6 @@ if __name__ == "__main__":
         warp_case(8, 256, 256)
         warp_case(32, 256, 256)
         warp_case(32, 256, 256, rough=True)
-    if which in ("all", "trunk"):   # generator trunk 128x128, N=16: fused single launch vs 33 per-layer launches
-        import ctypes
-        from tecogan_b200 import _ffi
-        L = 33
-        xin = torch.randn(1, 128, 128, 64, device="cuda").to(torch.bfloat16)
-        a, b = torch.zeros_like(xin), torch.zeros_like(xin)
-        ws = [K.packed_weight(torch.randn(3, 3, 64, 64, device="cuda") * 0.03, 64, 64) for _ in range(L)]
-        bs = [torch.zeros(64, device="cuda") for _ in range(L)]
-        wall, ball = torch.cat(ws).contiguous(), torch.cat(bs).contiguous()
-        flags = torch.zeros(128, device="cuda", dtype=torch.int32)
-
-        def fused():
-            _ffi.call("teco_trunk64_tc", 1, 128, 128, L, _ffi.ptr(xin), _ffi.ptr(a), _ffi.ptr(b), _ffi.ptr(wall), _ffi.ptr(ball),
-                      _ffi.ptr(flags), _ffi.stream_ptr())
-
-        def layered():
-            K.conv3x3_tc(xin, ws[0], bs[0], a, cout=64, act=1)
-            for i in range(1, L, 2):
-                K.conv3x3_tc(a, ws[i], bs[i], b, cout=64, act=1)
-                K.conv3x3_tc(b, ws[i + 1], bs[i + 1], a, cout=64, act=0, res=a)
-        if os.environ.get("TECO_TRUNK_STAMPS"):
-            fused(); torch.cuda.synchronize()
-            buf = torch.zeros(128 * 64, device="cuda", dtype=torch.int64)
-            _ffi.call("teco_debug_timing", _ffi.ptr(buf))
-            fused(); torch.cuda.synchronize()
-            _ffi.call("teco_debug_timing", _ffi.ptr(None))
-            st = buf.view(128, 8, 8).cpu().double()
-            names = ["flags_seen", "proxy_fence", "halo_landed", "mma_issued", "acc_ready", "stores_issued", "after_bar", "published"]
-            base = st[:, 2, 0:1]          # layer 2 flags_seen as origin
-            work = st[:, 3, 7] - st[:, 3, 0]            # own work of layer 3: flags seen -> published
-            wait = st[:, 4, 0] - st[:, 3, 7]            # then waiting for the nine flags of layer 3
-            halo = st[:, 3, 2] - st[:, 3, 0]
-            pub = st[:, 3, 7] - st[:, 3, 6]
-            for nm, v in (("own work", work), ("wait for neighbours", wait), ("halo load", halo), ("publish", pub)):
-                q = torch.quantile(v, torch.tensor([0.0, 0.1, 0.5, 0.9, 1.0], dtype=torch.float64))
-                print("  %-20s min %.0f  p10 %.0f  median %.0f  p90 %.0f  max %.0f" % ((nm,) + tuple(q.tolist())))
-            for l in (2, 3, 4):
-                rel = st[:, l, :] - base
-                print("layer %d: " % l + "  ".join("%s %.0f" % (nm, rel[:, i].median().item()) for i, nm in enumerate(names)))
-        for name, fn in (("fused trunk (1 launch)", fused), ("per-layer (33 launches)", layered)):
-            fn()
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
-            us = time_us(g.replay, reps=20, warm=3)
-            print("trunk 128x128 N=16, %s: %.1f us  (%.2f us / layer, %.0f TFLOP/s)" % (name, us, us / L, L * 1.208 / us * 1e3), flush=True)
     if which == "one":   # for ncu: a handful of launches of the dominant layer
         x = torch.randn(1, 128, 128, 64, device="cuda").to(torch.bfloat16)
         wpk = K.packed_weight(torch.randn(3, 3, 64, 64, device="cuda") * 0.05, 64, 64)
