@@ -227,6 +227,25 @@ int teco_loss_gan_f32(const float* d_fake, const float* d_real, float* out, floa
 int teco_adam_f32(float* p, float* m, float* v, const float* g, int64_t n, float lr_t, float b1, float b2, float eps,
                   float gscale, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Evaluation metrics on the device (reference metrics.py).  tgt / out: uint8 RGB frames
+ * [N,tH,tW,3] / [N,oH,oW,3] (the decoded PNGs; to_uint8(x,0,255) metrics.py:57-61 is the identity on them).
+ * (y0,x0,h,w) is the crop_8x8 window of metrics.py:77-92, the same offsets in both frames (the reference
+ * first cuts the output to the target size, metrics.py:134-135, which a window inside both frames covers).
+ * acc: N x 4 doubles {sum (Yt-Yp)^2, ~bits(min Yp), bits(max Yp), sum of SSIM map} -- 8-byte slots, the
+ * min / max of Y_pred held as (complemented) bit patterns so that zero is neutral for every slot.
+ * Y = 16 + 0.2568 R + 0.5041 G + 0.0979 B in float64, metrics.py:37-55 (_rgb2ycbcr, maxVal 255).
+ * ------------------------------------------------------------------------------------- */
+/* psnr() metrics.py:63-70: zeroes acc, then fills slots 0..2.  PSNR_n = 20 log10(255 / sqrt(acc[n][0] / (h*w))). */
+int teco_metrics_psnr_y_u8(const uint8_t* tgt, int32_t tH, int32_t tW, const uint8_t* out, int32_t oH, int32_t oW,
+                           int32_t N, int32_t y0, int32_t x0, int32_t h, int32_t w, double* acc, void* stream);
+/* ssim() metrics.py:72-75 = skimage compare_ssim(Y_true, Y_pred, data_range = max Yp - min Yp): 7x7 uniform
+ * window, sample covariance, K1 0.01, K2 0.03, mean over the (h-6) x (w-6) positions whose window lies inside.
+ * Needs slots 1..2 from teco_metrics_psnr_y_u8 on the same stream; adds into slot 3.
+ * SSIM_n = acc[n][3] / ((h-6)*(w-6)).  h or w below 7 -> TECO_E_INVALID (skimage raises ValueError). */
+int teco_metrics_ssim_y_u8(const uint8_t* tgt, int32_t tH, int32_t tW, const uint8_t* out, int32_t oH, int32_t oW,
+                           int32_t N, int32_t y0, int32_t x0, int32_t h, int32_t w, double* acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

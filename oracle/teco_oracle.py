@@ -732,6 +732,27 @@ def psnr_y(img_true_u8, img_pred_u8):
     return 20.0 * math.log10(255.0 / rmse)
 
 
+def ssim_y(img_true_u8, img_pred_u8):
+    """metrics.py:72-75: skimage.measure.compare_ssim(Y_true, Y_pred, data_range=Y_pred.max()-Y_pred.min()).
+    skimage is a third-party dependency that is not installed here (the reference imports skimage.measure.compare_ssim,
+    i.e. scikit-image <= 0.15); its published algorithm is restated: float64, 7x7 uniform window (scipy.ndimage.
+    uniform_filter), sample covariance (cov_norm = 49/48), K1 = 0.01, K2 = 0.03, mean of the S map cropped by 3 pixels.
+    Pinned in tests/test_oracle_golden.py against a second derivation by direct 49-term window sums."""
+    from scipy.ndimage import uniform_filter
+    X, Y = _y_of_u8(img_true_u8).astype(np.float64), _y_of_u8(img_pred_u8).astype(np.float64)
+    if min(X.shape) < 7:
+        raise ValueError("win_size exceeds image extent.")
+    R = float(Y.max() - Y.min())
+    NP = 49.0
+    cov_norm = NP / (NP - 1.0)
+    ux, uy = uniform_filter(X, size=7), uniform_filter(Y, size=7)
+    uxx, uyy, uxy = uniform_filter(X * X, size=7), uniform_filter(Y * Y, size=7), uniform_filter(X * Y, size=7)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    C1, C2 = (0.01 * R) ** 2, (0.03 * R) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    return float(S[3:-3, 3:-3].mean())
+
+
 def crop_8x8(img):
     """metrics.py:77-92."""
     oh, ow = img.shape[0], img.shape[1]

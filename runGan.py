@@ -4,8 +4,9 @@ Mirror of the reference's runGan.py launcher (run cases, reference runGan.py:1-1
 python3 runGan.py 1   # inference on LR/calendar with the flags of record (reference runGan.py:67-90)
 python3 runGan.py 3   # train TecoGAN  (reference runGan.py:107-244)
 python3 runGan.py 4   # train FRVSR    (reference runGan.py:247-296)
-Cases 0 (download, needs network) and 2 (metrics.py: LPIPS needs AlexNet weights) are outside the hot path
- and print why they are not run.
+python3 runGan.py 2   # PSNR / SSIM of ./results/<scene> against ./HR/<scene> on the GPU (reference runGan.py:92-105; the
+                      # LPIPS / tLP / tOF columns of the reference's metrics.py are outside the hot path)
+Case 0 (download, needs network) is outside the hot path and prints why it is not run.
 Extra arguments after the case number are appended to the main.py command line (e.g. --max_iter 100).
 '''
 import datetime
@@ -58,8 +59,11 @@ elif runcase == 1:   # inference a trained model
                 "--num_resblock", "16", "--checkpoint", ckpt, "--output_ext", "png"] + extra
         mycall(cmd1).communicate()
 elif runcase == 2:
-    print("case 2 runs metrics.py (PSNR/SSIM/LPIPS/tOF, reference runGan.py:92-105): out of the hot path; PSNR and tOF are "
-          "restated in oracle/teco_oracle.py for the parity tests.")
+    testpre = ["calendar"]                       # reference runGan.py:94-105
+    dirstr, tarstr = './results/', './HR/'
+    cmd1 = [sys.executable, os.path.join(HERE, "metrics.py"), "--output", dirstr + "metric_log/",
+            "--results", ",".join(dirstr + _ for _ in testpre), "--targets", ",".join(tarstr + _ for _ in testpre)] + extra
+    mycall(cmd1).communicate()
 elif runcase == 3:   # Train TecoGAN -- flags of record reference runGan.py:142-234
     now_str = datetime.datetime.now().strftime("%m-%d-%H")
     train_dir = "ex_TecoGAN%s/" % now_str

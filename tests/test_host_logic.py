@@ -145,3 +145,18 @@ def test_train_mode_refuses_to_run_without_data_or_vgg_unless_opted_in():
     assert F.train_precision == "fp32" and F.synthetic_data is False
     with pytest.raises(ValueError, match="input_video_dir is not provided"):
         main.train(F)
+
+
+def test_metrics_crop_window_matches_reference_crop_8x8_golden():
+    """tecogan_b200.metrics.crop_window (host arithmetic) against the offsets/sizes the reference's crop_8x8 produced."""
+    import os
+    import numpy as np
+    from tests.conftest import GOLDEN
+    from tecogan_b200.metrics import crop_8x8, crop_window
+    g = np.load(os.path.join(GOLDEN, "metrics.npz"), allow_pickle=False)
+    for i in range(int(g["n_cases"])):
+        t = g["tgt%d" % i]
+        assert crop_window(t.shape[0], t.shape[1]) == tuple(int(v) for v in g["crop%d" % i])
+        c, y, x = crop_8x8(t)
+        assert c.shape[:2] == tuple(int(v) for v in g["crop%d" % i][2:])
+    assert crop_window(144, 180) == (8, 10, 128, 160) and crop_window(32, 32)[2:] == (0, 0)

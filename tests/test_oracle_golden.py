@@ -195,3 +195,52 @@ def test_tfext_legacy_resize_batchnorm_pool_s2d():
     y = _rnd(8, 2, 8, 12, 3)
     np.testing.assert_array_equal(O.space_to_depth4(y).numpy(), X.space_to_depth(y.numpy(), 4))
     np.testing.assert_array_equal(O.lrelu(x, 0.2).numpy(), X.leaky_relu(x.numpy(), 0.2))
+
+
+# ---- evaluation metrics: the oracle against the reference's own psnr / crop_8x8 / _rgb2ycbcr outputs
+# (tests/golden/make_golden_metrics.py executes those functions out of /root/reference/metrics.py) --------------------
+def _metric_cases():
+    g = _load("metrics")
+    for i in range(int(g["n_cases"])):
+        yield i, g
+
+
+def test_metrics_psnr_crop_and_y_match_the_reference_functions():
+    for i, g in _metric_cases():
+        tgt, out = g["tgt%d" % i], g["out%d" % i]
+        y, x, h, w = (int(v) for v in g["crop%d" % i])
+        ct, co = O.crop_8x8(tgt), O.crop_8x8(out)
+        assert ct.shape[:2] == (h, w) and np.array_equal(ct, tgt[y:y + h, x:x + w])
+        assert abs(O.psnr_y(tgt, out) - float(g["psnr_full%d" % i])) < 1e-9
+        assert abs(O.psnr_y(ct, co) - float(g["psnr_crop%d" % i])) < 1e-9
+        if "y_full%d" % i in g.files:
+            np.testing.assert_allclose(O._y_of_u8(out), g["y_full%d" % i], rtol=0, atol=1e-10)
+
+
+def _ssim_direct(tgt, out):
+    """Second derivation of compare_ssim's defaults from its definition: explicit 49-term sums per window position,
+    sample (co)variances with the 1/(NP-1) normalisation, no filtering library."""
+    X, Y = O._y_of_u8(tgt).astype(np.float64), O._y_of_u8(out).astype(np.float64)
+    R = Y.max() - Y.min()
+    C1, C2 = (0.01 * R) ** 2, (0.03 * R) ** 2
+    H, W = X.shape
+    tot, n = 0.0, 0
+    for r in range(H - 6):
+        for c in range(W - 6):
+            a, b = X[r:r + 7, c:c + 7].ravel(), Y[r:r + 7, c:c + 7].ravel()
+            ua, ub = a.mean(), b.mean()
+            va, vb = ((a - ua) ** 2).sum() / 48.0, ((b - ub) ** 2).sum() / 48.0
+            vab = ((a - ua) * (b - ub)).sum() / 48.0
+            tot += ((2 * ua * ub + C1) * (2 * vab + C2)) / ((ua * ua + ub * ub + C1) * (va + vb + C2))
+            n += 1
+    return tot / n
+
+
+def test_metrics_ssim_restatement_equals_the_direct_definition():
+    g = _load("metrics")
+    tgt, out = g["tgt3"][:40, :37], g["out3"][:40, :37]
+    assert abs(O.ssim_y(tgt, out) - _ssim_direct(tgt, out)) < 1e-9
+    assert abs(O.ssim_y(tgt, tgt) - 1.0) < 1e-12
+    import pytest
+    with pytest.raises(ValueError):
+        O.ssim_y(tgt[:6], out[:6])
