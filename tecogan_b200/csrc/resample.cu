@@ -3,6 +3,7 @@
 // resize, max-pool, space-to-depth, Gaussian down-sampling.  Reference call sites are cited in
 // include/teco.h next to each entry point.
 #include "teco_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -654,6 +655,13 @@ int teco_warp_bwd_f32(const float* img, const float* flow, const float* dout, fl
   return TECO_OK;
 }
 
+}  // extern "C"
+// warp_s2d_v2.cu: the low-instruction-count version for the inference layout (bf16 destination, aligned channel offset)
+bool teco_warp_s2d_v2_applicable(const void* dst, int dst_cpitch, int ch_off, int dst_bf16, const float* warped_out);
+int teco_warp_s2d_v2_launch(const float* pre_gen, const float* flow_lr, void* dst, int N, int h, int w, int fh, int fw,
+                            int dst_cpitch, int ch_off, float in_scale, float in_shift, cudaStream_t stream);
+extern "C" {
+
 int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, float* warped_out, int32_t N, int32_t h,
                         int32_t w, int32_t fh, int32_t fw, int32_t dst_cpitch, int32_t ch_off, int32_t dst_bf16,
                         float in_scale, float in_shift, void* stream) {
@@ -662,6 +670,12 @@ int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, f
                  "teco_warp_s2d_fused: bad shape h=%d w=%d fh=%d fw=%d", h, w, fh, fw);
   TECO_CHECK_ARG(ch_off >= 0 && ch_off + 48 <= dst_cpitch, "teco_warp_s2d_fused: 48 channels do not fit at ch_off=%d in pitch %d",
                  ch_off, dst_cpitch);
+  TECO_CHECK_ARG((((uintptr_t)pre_gen) & 15) == 0, "teco_warp_s2d_fused: pre_gen must be 16-byte aligned");
+  const char* v2_env = getenv("TECO_WARP_V2");                 // A/B switch, read per call: "0" selects the first version
+  const bool use_v2 = !v2_env || v2_env[0] != '0';
+  if (use_v2 && teco_warp_s2d_v2_applicable(dst, dst_cpitch, ch_off, dst_bf16, warped_out))
+    return teco_warp_s2d_v2_launch(pre_gen, flow_lr, dst, N, h, w, fh, fw, dst_cpitch, ch_off, in_scale, in_shift,
+                                   (cudaStream_t)stream);
   const int tiles_x = teco_ceil_div(w, WS_TLW), tiles_y = teco_ceil_div(h, WS_TLH);
   TECO_CHECK_ARG(tiles_y <= 65535 && N <= 65535, "teco_warp_s2d_fused: more than 65535 row bands or images");
   const size_t smem = WS_SMEM_FLOATS * sizeof(float);
