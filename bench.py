@@ -398,11 +398,17 @@ def main():
     yy, xx = torch.meshgrid(torch.linspace(0, 6.28, wh, device=dev), torch.linspace(0, 6.28, wh, device=dev), indexing="ij")
     w_flow = torch.stack((1.5 + 0.5 * torch.sin(yy + xx), -0.75 + 0.5 * torch.cos(yy - xx)), dim=-1).expand(wn, wh, wh, 2).contiguous()
     w_dst = torch.zeros(wn, wh, wh, 64, device=dev, dtype=torch.bfloat16)
-    for _ in range(3):
-        K.warp_s2d_fused(w_pre, w_flow, w_dst, 0)
-    warp_us = ev_time(lambda: [K.warp_s2d_fused(w_pre, w_flow, w_dst, 0) for _ in range(5)]) * 1000.0 / 5
+    def warp_time(flow):
+        for _ in range(3):
+            K.warp_s2d_fused(w_pre, flow, w_dst, 0)
+        return ev_time(lambda: [K.warp_s2d_fused(w_pre, flow, w_dst, 0) for _ in range(5)]) * 1000.0 / 5
+    warp_us = warp_time(w_flow)
+    # the same with a rough motion field: +-1.5 LR pixels of independent noise per flow sample (source windows 12 HR pixels
+    # wider and taller than the tile, staged per half tile)
+    w_rough = (w_flow + 3.0 * (torch.rand(wh, wh, 2, device=dev) - 0.5)).contiguous()
+    warp_rough_us = warp_time(w_rough)
     warp_bytes = wn * (4 * wh) * (4 * wh) * 18.5
-    del w_pre, w_flow, w_dst
+    del w_pre, w_flow, w_rough, w_dst
 
     ms_res, ms_e2e = max_over_ranks([ms_res, ms_e2e])
     frames_total = B * CLIP_T * args.steps * world
@@ -435,11 +441,13 @@ def main():
                                           "achieved": layer_flop / (per_layer_us * 1e-6) / 1e12, "frac": layer_flop / (per_layer_us * 1e-6) / 1e12 / peak_tf},
                      "whole_step": {"algorithmic_gflop_per_clip": clip_flop() / 1e9, "achieved_tflops": whole_tf,
                                     "frac_of_sustained": whole_tf / peak_tf_sus}},
-        "roofline_hbm": {"bound": "hbm", "kernel": "warp_s2d_fused_kernel (upscale_four + dense_image_warp + space_to_depth), "
-                                                     "32 x 1024x1024 HR frames, smooth motion field, working set 604 MB > L2",
+        "roofline_hbm": {"bound": "hbm", "kernel": "warp_s2d_v2_kernel behind teco_warp_s2d_fused (upscale_four + dense_image_warp + "
+                                                     "space_to_depth), 32 x 1024x1024 HR frames, smooth motion field, working set 604 MB > L2",
                          "achieved": warp_bytes / (warp_us * 1e-6) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                          "frac": warp_bytes / (warp_us * 1e-6) / 1e9 / peak_gbs, "us_per_launch": warp_us,
-                         "algorithmic_bytes_per_launch": warp_bytes, "traffic": _traffic("r02_warp_traffic.json"),
+                         "algorithmic_bytes_per_launch": warp_bytes, "traffic": _traffic("r02_warp_v2_traffic.json"),
+                         "rough_motion": {"us_per_launch": warp_rough_us, "achieved": warp_bytes / (warp_rough_us * 1e-6) / 1e9,
+                                          "frac": warp_bytes / (warp_rough_us * 1e-6) / 1e9 / peak_gbs},
                          "peak_source": peak_src + ", copy bandwidth"},
         "wall_s_resident_leg": wall_res,
     }

@@ -1,8 +1,5 @@
 """Run-time configuration of the compute path (not part of the reference interface)."""
-import os as _os
-
-_cfg = {"precision": "bf16", "train_precision": "fp32", "lin_trunk": _os.environ.get("TECO_LIN_TRUNK", "1") == "1",
-        "tail_chunk": int(_os.environ.get("TECO_TAIL_CHUNK", "0"))}
+_cfg = {"precision": "bf16", "train_precision": "fp32", "lin_trunk": __import__("os").environ.get("TECO_LIN_TRUNK", "1") == "1"}
 
 
 def set_precision(p):
@@ -41,15 +38,3 @@ def set_lin_trunk(on):
 
 def lin_trunk():
     return _cfg["lin_trunk"]
-
-
-def set_tail_chunk(clips):
-    """Clip batches whose 64-channel HR intermediate exceeds the L2 (296 clips of 32x32: 621 MB against 126 MB): run the
-    generator's HR tail (bicubic, conv_tran1, conv_tran2, output conv, deprocess) in chunks of `clips` clips through ONE
-    chunk-sized scratch that is rewritten chunk after chunk, so the intermediate lives in L2 and never reaches HBM.
-    0 = whole batch per launch."""
-    _cfg["tail_chunk"] = max(0, int(clips))
-
-
-def tail_chunk():
-    return _cfg["tail_chunk"]

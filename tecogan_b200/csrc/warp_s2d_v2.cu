@@ -16,12 +16,13 @@
 //   * results go through a bf16 staging tile in shared memory in destination order and leave as 16-byte stores, six per LR
 //     pixel (was: three shuffles, eight selects and an 8-byte store per HR pixel with a quarter of the lanes idle).
 #include "teco_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
 constexpr int V2_TPB = 256;
 constexpr int V2_TLH = 4, V2_TLW = 32;                       // LR tile; thread = one HR column x two LR rows (8 HR pixels)
-constexpr int V2_WIN_FLOATS = 9 * 1024;                      // 36 KB source window: 21 rows x 140 px of fp32 RGB fit
+constexpr int V2_WIN_FLOATS = 10 * 1024;                     // 40 KB source window: 24 rows x 140 px of fp32 RGB fit
 constexpr int V2_STAGE_BYTES = V2_TLH * V2_TLW * 96;         // 12 KB: 48 bf16 per LR pixel
 constexpr int V2_NSAMP = (V2_TLH + 1) * (V2_TLW + 1);        // 165 flow samples bound every HR flow vector of the tile
 constexpr float V2_MAGIC = 12582912.f;                       // 1.5 * 2^23
@@ -35,26 +36,62 @@ __device__ __forceinline__ float key2f(int k) { return __int_as_float(k ^ ((k >>
 
 struct V2Smem {
   float2 flow[V2_NSAMP + 3];      // 4 * flow_lr at (ly0 + r, lx0 + j), clamped like upscale_four, symmetric pad applied
+  unsigned long long bar;         // mbarrier of the window's bulk copies
+  float mm[4];                    // min fy, max fy, min fx, max fx over the tile's flow samples
   int win[5];                     // y_lo, x_lo, rows, floats per window row, flags (1 staged, 2 interior in y, 4 interior in x)
 };
 
-struct V2Thread {                 // per-thread state of the pixel loop
-  float Fy[3], Fx[3];             // x-interpolated flow of the three LR sample rows around this thread's two LR rows
-  float Yf, Xf, hy, hx, in_scale, in_shift;
+struct V2Thread {                 // per-thread constants of the pixel loop
+  float Xf, hy, hx, in_scale, in_shift;
   int pitch;
   unsigned cbase;
-  unsigned char* srow;
 };
 
-// Eight HR pixels of one thread.  IY / IX: no query of the tile can touch a clamp on that axis (CTA-uniform), so the floor
-// needs no clamp and the fraction is already in [0,1) -- as template parameters because ptxas otherwise predicates both
-// variants into every pixel.
-template <bool IY, bool IX>
-__device__ __forceinline__ void v2_pixels(const float* __restrict__ base, const V2Thread& t) {
+struct V2Window { int y_lo, x_lo, rows, rowf, flags; };
+
+// Window of the previous HR frame that holds every query of HR rows [Yt, Yt + nrows) x columns [X0, X0 + 128) given the bounds
+// of the flow over the tile (same construction as the first version): queries Y - fy lie in [Yt - mxy, Yt + nrows - 1 - mny],
+// the floor is clamped to [0, H-2], plus the +1 neighbour row; columns alike.
+__device__ __forceinline__ V2Window v2_window(float mny, float mxy, float mnx, float mxx, int Yt, int nrows, int X0, int H, int W) {
+  const float hy = (float)(H - 2), hx = (float)(W - 2);
+  const float qy_lo = (float)Yt - mxy, qy_hi = (float)(Yt + nrows - 1) - mny;
+  const float qx_lo = (float)X0 - mxx, qx_hi = (float)(X0 + 4 * V2_TLW - 1) - mnx;
+  V2Window v;
+  v.y_lo = (int)fminf(fmaxf(floorf(qy_lo) - 1.f, 0.f), hy);
+  const int y_hi = (int)fminf(fmaxf(floorf(qy_hi) + 1.f, 0.f), hy) + 1;
+  v.x_lo = (int)fminf(fmaxf(floorf(qx_lo) - 1.f, 0.f), hx) & ~3;               // whole groups of four pixels (48 bytes):
+  const int x_hi = min(((int)fminf(fmaxf(floorf(qx_hi) + 1.f, 0.f), hx) + 1) | 3, W - 1);   // 16-byte aligned window rows
+  v.rows = y_hi - v.y_lo + 1;
+  v.rowf = (x_hi - v.x_lo + 1) * 3;
+  v.flags = v.rows * v.rowf <= V2_WIN_FLOATS ? 1 : 0;
+  // no query can touch a clamp on this axis: the floor needs no clamp and the fraction is already in [0,1)
+  v.flags |= (qy_lo >= 1.f && qy_hi <= (float)(H - 3)) ? 2 : 0;
+  v.flags |= (qx_lo >= 1.f && qx_hi <= (float)(W - 3)) ? 4 : 0;
+  return v;
+}
+
+// One warp stages a window: one bulk copy (TMA engine, no register or LSU traffic) per window row, all signalling `bar`.
+__device__ __forceinline__ void v2_stage(const float* img, int W, const V2Window& v, float* win, uint32_t bar, int lane) {
+  const uint32_t row_bytes = (uint32_t)v.rowf * 4u;
+  if (lane == 0) tcptx::mbar_expect_tx(bar, (uint32_t)v.rows * row_bytes);
+  __syncwarp();
+  const float* src0 = img + ((size_t)v.y_lo * W + v.x_lo) * 3;
+  const uint32_t sbase = tcptx::smem_u32(win);
+  for (int r = lane; r < v.rows; r += 32)
+    tcptx::bulk_load_1d(sbase + (uint32_t)r * row_bytes, src0 + (size_t)r * (W * 3), row_bytes, bar);
+}
+
+// NK LR rows (4 NK HR pixels) of one thread's HR column.  Fy / Fx: x-interpolated flow of the NK + 1 LR sample rows around
+// them; Yf: HR row of the first pixel; srow: this thread's slot of the first LR row in the staging tile.
+// IY / IX: no query of the tile can touch a clamp on that axis (CTA-uniform) -- template parameters because ptxas otherwise
+// predicates both variants into every pixel.
+template <bool IY, bool IX, int NK>
+__device__ __forceinline__ void v2_pixels(const float* __restrict__ base, const V2Thread& t, const float* Fy, const float* Fx,
+                                          float Yf, unsigned char* srow) {
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float Ty = t.Fy[k], Dy = t.Fy[k + 1] - Ty, Tx = t.Fx[k], Dx = t.Fx[k + 1] - Tx;
-    const float Yk = t.Yf + (float)(4 * k);
+  for (int k = 0; k < NK; ++k) {
+    const float Ty = Fy[k], Dy = Fy[k + 1] - Ty, Tx = Fx[k], Dx = Fx[k + 1] - Tx;
+    const float Yk = Yf + (float)(4 * k);
 #pragma unroll
     for (int dy = 0; dy < 4; ++dy) {
       // flow = T + (B - T) * (dy / 4);  query = grid - flow
@@ -89,12 +126,18 @@ __device__ __forceinline__ void v2_pixels(const float* __restrict__ base, const 
         o[c] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
       }
       // space-to-depth: element (dy*4 + dx)*3 + c of the 48 channels of LR pixel (ly, lx)
-      unsigned short* d = reinterpret_cast<unsigned short*>(t.srow + k * (V2_TLW * 96) + dy * 24);
+      unsigned short* d = reinterpret_cast<unsigned short*>(srow + k * (V2_TLW * 96) + dy * 24);
       d[0] = o[0];
       d[1] = o[1];
       d[2] = o[2];
     }
   }
+}
+
+__device__ __forceinline__ void v2_set_base(V2Thread& t, bool staged, const V2Window& v, int W) {
+  t.pitch = staged ? v.rowf : W * 3;
+  t.cbase = 0u - ((unsigned)(V2_MAGIC_BITS + (staged ? v.y_lo : 0)) * (unsigned)t.pitch +
+                  (unsigned)(V2_MAGIC_BITS + (staged ? v.x_lo : 0)) * 3u);
 }
 
 __global__ void __launch_bounds__(V2_TPB, 4)
@@ -109,11 +152,13 @@ warp_s2d_v2_kernel(const float* __restrict__ pre_gen, const float* __restrict__ 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float* img = pre_gen + (size_t)n * H * W * 3;
   const int Y0 = 4 * ly0, X0 = 4 * lx0;
-  V2Thread t;
-  t.hy = (float)(H - 2);
-  t.hx = (float)(W - 2);
+  const uint32_t bar = tcptx::smem_u32(&S.bar);
 
   // ---- (1) the 5 x 33 flow samples of the tile -> shared memory
+  if (tid == 0) {
+    tcptx::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (tid < V2_NSAMP) {
     const float* fb = flow_lr + (size_t)n * fh * fw * 2;
     const int r = tid / (V2_TLW + 1), j = tid - r * (V2_TLW + 1);
@@ -126,14 +171,12 @@ warp_s2d_v2_kernel(const float* __restrict__ pre_gen, const float* __restrict__ 
   }
   __syncthreads();
 
-  // ---- (2) warp 0: bounds of the flow over the tile -> the window of the previous HR frame that holds every query (same
-  // bounds as the first version).  The other warps go on to (3) meanwhile.
+  // ---- (2) warp 0: bounds of the flow over the tile -> window -> bulk copies in flight.  The other warps go on to (3).
   if (wid == 0) {
     int kmin_y = 0x7fffffff, kmax_y = (int)0x80000000, kmin_x = 0x7fffffff, kmax_x = (int)0x80000000;
 #pragma unroll
     for (int s = 0; s < (V2_NSAMP + 31) / 32; ++s) {
-      const int i = min(lane + 32 * s, V2_NSAMP - 1);
-      const float2 f = S.flow[i];
+      const float2 f = S.flow[min(lane + 32 * s, V2_NSAMP - 1)];
       const int ky = f2key(f.x), kx = f2key(f.y);
       kmin_y = min(kmin_y, ky);
       kmax_y = max(kmax_y, ky);
@@ -142,67 +185,79 @@ warp_s2d_v2_kernel(const float* __restrict__ pre_gen, const float* __restrict__ 
     }
     const float mny = key2f(__reduce_min_sync(0xffffffffu, kmin_y)), mxy = key2f(__reduce_max_sync(0xffffffffu, kmax_y));
     const float mnx = key2f(__reduce_min_sync(0xffffffffu, kmin_x)), mxx = key2f(__reduce_max_sync(0xffffffffu, kmax_x));
-    // queries: Y - fy in [Y0 - mxy, Y0 + 15 - mny]; floor clamped to [0, H-2], plus the +1 neighbour row
-    const float qy_lo = (float)Y0 - mxy, qy_hi = (float)(Y0 + 4 * V2_TLH - 1) - mny;
-    const float qx_lo = (float)X0 - mxx, qx_hi = (float)(X0 + 4 * V2_TLW - 1) - mnx;
-    const int y_lo = (int)fminf(fmaxf(floorf(qy_lo) - 1.f, 0.f), t.hy);
-    const int y_hi = (int)fminf(fmaxf(floorf(qy_hi) + 1.f, 0.f), t.hy) + 1;
-    const int x_lo = (int)fminf(fmaxf(floorf(qx_lo) - 1.f, 0.f), t.hx) & ~3;   // whole groups of four pixels (48 bytes):
-    const int x_hi = min(((int)fminf(fmaxf(floorf(qx_hi) + 1.f, 0.f), t.hx) + 1) | 3, W - 1);   // 16-byte aligned rows
-    const int rows = y_hi - y_lo + 1, rowf = (x_hi - x_lo + 1) * 3;
-    int flags = rows * rowf <= V2_WIN_FLOATS ? 1 : 0;
-    flags |= (qy_lo >= 1.f && qy_hi <= (float)(H - 3)) ? 2 : 0;
-    flags |= (qx_lo >= 1.f && qx_hi <= (float)(W - 3)) ? 4 : 0;
-    if (lane == 0) { S.win[0] = y_lo; S.win[1] = x_lo; S.win[2] = rows; S.win[3] = rowf; S.win[4] = flags; }
+    const V2Window v = v2_window(mny, mxy, mnx, mxx, Y0, 4 * V2_TLH, X0, H, W);
+    if (lane == 0) {
+      S.mm[0] = mny; S.mm[1] = mxy; S.mm[2] = mnx; S.mm[3] = mxx;
+      S.win[0] = v.y_lo; S.win[1] = v.x_lo; S.win[2] = v.rows; S.win[3] = v.rowf; S.win[4] = v.flags;
+    }
+    if (v.flags & 1) v2_stage(img, W, v, win, bar, lane);
   }
 
   // ---- (3) this thread: HR column X = X0 + xl of LR rows ly0 + 2 rh, + 1.  flow = upscale_four(4 flow_lr) written as
   // T + (B - T) * (dy / 4) per component with T / B the x-interpolated samples of the LR rows above / below.
   const int xl = tid & (4 * V2_TLW - 1), rh = tid >> 7;
   const int lxl = xl >> 2, dx = xl & 3;
-  {
-    const float wx1 = 0.25f * (float)dx, wx0 = 1.f - wx1;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const float2 a = S.flow[(2 * rh + r) * (V2_TLW + 1) + lxl], b = S.flow[(2 * rh + r) * (V2_TLW + 1) + lxl + 1];
-      t.Fy[r] = a.x * wx0 + b.x * wx1;
-      t.Fx[r] = a.y * wx0 + b.y * wx1;
-    }
-  }
-  t.Yf = (float)(Y0 + 8 * rh);
+  const float wx1 = 0.25f * (float)dx, wx0 = 1.f - wx1;
+  V2Thread t;
+  t.hy = (float)(H - 2);
+  t.hx = (float)(W - 2);
   t.Xf = (float)(X0 + xl);
   t.in_scale = in_scale;
   t.in_shift = in_shift;
-  t.srow = stage + ((2 * rh) * V2_TLW + lxl) * 96 + dx * 6;
-  __syncthreads();
-  const int y_lo = S.win[0], x_lo = S.win[1], rows = S.win[2], rowf = S.win[3], flags = S.win[4];
-  const bool use_smem = flags & 1;
-
-  if (use_smem) {                 // the whole window in flight at once: 16-byte cp.async, a warp per window row
-    const int cpr = rowf >> 2;
-    const float* src0 = img + ((size_t)y_lo * W + x_lo) * 3;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(win);
-    for (int r = wid; r < rows; r += V2_TPB / 32) {
-      const float* src = src0 + (size_t)r * (W * 3);
-      const uint32_t drow = sbase + (uint32_t)(r * rowf) * 4u;
-      for (int k = lane; k < cpr; k += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(drow + 16u * k), "l"(src + 4 * k) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    t.pitch = rowf;
-    t.cbase = 0u - ((unsigned)(V2_MAGIC_BITS + y_lo) * (unsigned)rowf + (unsigned)(V2_MAGIC_BITS + x_lo) * 3u);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else {
-    t.pitch = W * 3;
-    t.cbase = 0u - ((unsigned)V2_MAGIC_BITS * (unsigned)(W * 3) + (unsigned)V2_MAGIC_BITS * 3u);
+  float Fy[3], Fx[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float2 a = S.flow[(2 * rh + r) * (V2_TLW + 1) + lxl], b = S.flow[(2 * rh + r) * (V2_TLW + 1) + lxl + 1];
+    Fy[r] = a.x * wx0 + b.x * wx1;
+    Fx[r] = a.y * wx0 + b.y * wx1;
   }
+  unsigned char* scol = stage + lxl * 96 + dx * 6;          // this thread's column slot in LR row 0 of the staging tile
   __syncthreads();
+  V2Window v;
+  v.y_lo = S.win[0]; v.x_lo = S.win[1]; v.rows = S.win[2]; v.rowf = S.win[3]; v.flags = S.win[4];
 
-  if (!use_smem) v2_pixels<false, false>(img, t);   // window too large for shared memory (very rough flow): gather through L1
-  else if ((flags & 6) == 6) v2_pixels<true, true>(win, t);
-  else if (flags & 2) v2_pixels<true, false>(win, t);
-  else if (flags & 4) v2_pixels<false, true>(win, t);
-  else v2_pixels<false, false>(win, t);
+  if (v.flags & 1) {
+    // the window fits: 8 pixels per thread straight from shared memory
+    v2_set_base(t, true, v, W);
+    const float Yf = (float)(Y0 + 8 * rh);
+    unsigned char* srow = scol + (2 * rh) * (V2_TLW * 96);
+    tcptx::mbar_wait_warp(bar, 0);
+    if ((v.flags & 6) == 6) v2_pixels<true, true, 2>(win, t, Fy, Fx, Yf, srow);
+    else if (v.flags & 2) v2_pixels<true, false, 2>(win, t, Fy, Fx, Yf, srow);
+    else if (v.flags & 4) v2_pixels<false, true, 2>(win, t, Fy, Fx, Yf, srow);
+    else v2_pixels<false, false, 2>(win, t, Fy, Fx, Yf, srow);
+  } else {
+    // rough flow: the tile in two halves of 2 LR rows (thread = HR column x ONE LR row per half), each with its own smaller
+    // window; a half whose window still does not fit gathers from global memory through L1
+    const float mny = S.mm[0], mxy = S.mm[1], mnx = S.mm[2], mxx = S.mm[3];
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const V2Window hv = v2_window(mny, mxy, mnx, mxx, Y0 + 8 * half, 8, X0, H, W);
+      const bool staged = hv.flags & 1;
+      if (staged) {
+        __syncthreads();                                   // every reader of the previous half's window is done
+        if (wid == 0) {
+          tcptx::fence_async_smem();
+          v2_stage(img, W, hv, win, bar, lane);
+        }
+      }
+      const int lr = 2 * half + rh;                        // this thread's LR row of the tile
+      float Gy[2], Gx[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float2 a = S.flow[(lr + r) * (V2_TLW + 1) + lxl], b = S.flow[(lr + r) * (V2_TLW + 1) + lxl + 1];
+        Gy[r] = a.x * wx0 + b.x * wx1;
+        Gx[r] = a.y * wx0 + b.y * wx1;
+      }
+      v2_set_base(t, staged, hv, W);
+      if (staged) {
+        tcptx::mbar_wait_warp(bar, phase);
+        phase ^= 1;
+      }
+      v2_pixels<false, false, 1>(staged ? win : img, t, Gy, Gx, (float)(Y0 + 4 * lr), scol + lr * (V2_TLW * 96));
+    }
+  }
   __syncthreads();
 
   // ---- (4) staged tile -> destination: 96 contiguous bytes per LR pixel as six 16-byte stores
@@ -214,8 +269,8 @@ warp_s2d_v2_kernel(const float* __restrict__ pre_gen, const float* __restrict__ 
     const int p = q / 6, part = q - p * 6;
     const int r = p >> 5, c = p & 31;
     if (ly0 + r < h && lx0 + c < w) {
-      const uint4 v = *reinterpret_cast<const uint4*>(stage + q * 16);
-      *reinterpret_cast<uint4*>(dtile + r * rpitch + c * ppitch + part * 16) = v;
+      const uint4 v4 = *reinterpret_cast<const uint4*>(stage + q * 16);
+      *reinterpret_cast<uint4*>(dtile + r * rpitch + c * ppitch + part * 16) = v4;
     }
   }
 }

@@ -292,19 +292,15 @@ class ClipEngine:
             _f32_slice_to_bf16(self.clip_in[t - 1], 0, 3, f.x_in, 0)
             _f32_slice_to_bf16(self.clip_in[t], 0, 3, f.x_in, 3)
             f.run(flow_out=self.flows[t - 1])
-        per_clip = self.out01[0].numel()
+        n = self.out01.numel()
         for t in range(T):
             if t == 0:
                 g.x_in[..., S2D_OFF:S2D_OFF + 48].zero_()
             else:
                 K.warp_s2d_fused(g.out, self.flows[t - 1], g.x_in, S2D_OFF, in_scale=0.5, in_shift=0.5)
             _f32_slice_to_bf16(self.clip_in[t], 0, 3, g.x_in, LR_OFF)
-            u8_t = self.clip_u8[t]
-
-            def deprocess(c0, c1):      # save_img quantisation of the clips that are finished (still in L2 when chunked)
-                call("teco_deprocess_u8", ptr(g.out[c0:c1], f32), ptr(self.out01[c0:c1], f32), ptr(u8_t[c0:c1], torch.uint8),
-                     (c1 - c0) * per_clip, stream_ptr())
-            g.run(self.clip_in[t], 3, after_chunk=deprocess)
+            g.run(self.clip_in[t], 3)
+            call("teco_deprocess_u8", ptr(g.out, f32), ptr(self.out01, f32), ptr(self.clip_u8[t], torch.uint8), n, stream_ptr())
 
     def replay(self):
         """Process the clip batch already in self.clip_in."""

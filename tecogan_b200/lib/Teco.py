@@ -461,7 +461,7 @@ class _TrainState:
                                 k + slot, str(tuple(self.store[k].shape)), str(tuple(v.shape))))
                         buf[o:o + n].copy_(v.reshape(-1).to(dtype=torch.float32))
             t = fetch("teco_b200/adam_steps_" + tag)
-            opt.t = int(t) if t is not None else self.global_step     # TF checkpoints: every optimiser stepped each iteration
+            opt.t = int(t) if t is not None else self._tf_adam_steps(get, tag, opt)
         v = fetch("teco_b200/tb_ema")
         if v is not None:
             self.tb_ema = float(v)
@@ -471,7 +471,28 @@ class _TrainState:
         v = fetch("teco_b200/d_counters")
         if v is not None:
             self.counter1, self.counter2 = int(v[0]), int(v[1])
+        else:                                   # a reference checkpoint keeps them as graph variables (lib/Teco.py:456-459)
+            c1, c2 = get("generator_train/gen_train_with_D_counter"), get("generator_train/gen_train_wo_D_counter")
+            if c1 is not None and c2 is not None:
+                self.counter1, self.counter2 = int(torch.as_tensor(c1)), int(torch.as_tensor(c2))
         return missing
+
+    def _tf_adam_steps(self, get, tag, opt):
+        """Step count of one optimiser when resuming from a checkpoint written by the REFERENCE.  TensorFlow keeps it as
+        beta1_power = beta1^(t+1) (AdamOptimizer._finish multiplies after every apply).  All three apply_gradients calls sit
+        in variable_scope('generator_train') (lib/Teco.py:438-481), created in the order discriminator, generator, fnet inside
+        train_gen_withD, hence the suffixes.  The generator and fnet step every iteration (= global_step); the discriminator
+        only when t_balance < Dbalance, i.e. gen_train_with_D_counter times (lib/Teco.py:456,464)."""
+        import math
+        suffix = {"d": "", "g": "_1", "f": "_2"} if self.GAN else {"g": "", "f": "_1"}
+        bp = get("generator_train/beta1_power" + suffix.get(tag, ""))
+        if bp is not None and 0.0 < float(torch.as_tensor(bp)) < 1.0 and 0.0 < opt.b1 < 1.0:
+            return max(0, int(round(math.log(float(torch.as_tensor(bp))) / math.log(opt.b1))) - 1)
+        if tag == "d":
+            c1 = get("generator_train/gen_train_with_D_counter")
+            if c1 is not None:
+                return int(torch.as_tensor(c1))
+        return self.global_step
 
     def update_list_avg(self):
         avg = list(self.loss_ema or [])

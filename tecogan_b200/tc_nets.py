@@ -126,12 +126,6 @@ class GeneratorPlan:
         self.bic = torch.zeros((B, 4 * h, 4 * w, 3), device=device, dtype=f32)
         self.out = torch.zeros((B, 4 * h, 4 * w, 3), device=device, dtype=f32)
         self.launches = 2 * num_resblock + 5 + 1
-        # HR tail in L2-sized chunks of clips (config.set_tail_chunk): chunk-sized scratch rewritten chunk after chunk
-        self.chunk = config.tail_chunk() if 0 < config.tail_chunk() < B else 0
-        if self.chunk:
-            c = self.chunk
-            self.u1s, self.u2s = z(c, 2 * h, 2 * w, 64), z(c, 4 * h, 4 * w, 64)
-            self.bic_s = torch.zeros((c, 4 * h, 4 * w, 3), device=device, dtype=f32)
         # 32-pixel-wide frames in a batch: the whole trunk as one launch of the row-linearised kx-fused kernel
         self.lin = config.lin_trunk() and B >= 8 and K.conv3x3_lin_supported(B, h, w, 2 * num_resblock + 1)
         if self.lin:
@@ -141,36 +135,16 @@ class GeneratorPlan:
             # buffer ids: 0 = x_in, 1 = a, 2 = b.  input conv x_in -> a (ReLU); block: a -> b (ReLU), b -> a (+ a)
             self.trunk_plan = [(0, 1, -1, ACT_RELU)] + [(1, 2, -1, ACT_RELU), (2, 1, 1, ACT_NONE)] * num_resblock
             self.launches = 1 + 4 + 1
-        if self.chunk:
-            self.launches += 4 * (-(-B // self.chunk) - 1)
 
     def run_bicubic(self, lr_f32, lr_cpitch=3):
         """bicubic_four(LR) for the output stage (lib/frvsr.py:84-86); independent of everything but the LR frame."""
         call("teco_bicubic4_f32", ptr(lr_f32, f32), ptr(self.bic, f32), self.B, self.h, self.w, 3, lr_cpitch, stream_ptr())
 
-    def _tail_chunked(self, lr_f32, lr_cpitch, after_chunk):
-        """bicubic -> conv_tran1 -> conv_tran2 -> output conv (-> after_chunk(c0, c1)) per chunk of clips: the same kernels
-        on the same data as the whole-batch launches (clips are independent), so the results are bit-identical."""
-        C = self.chunk
-        for c0 in range(0, self.B, C):
-            c1 = min(self.B, c0 + C)
-            n = c1 - c0
-            u1, u2, bic = self.u1s[:n], self.u2s[:n], self.bic_s[:n]
-            call("teco_bicubic4_f32", ptr(lr_f32[c0:c1], f32), ptr(bic, f32), n, self.h, self.w, 3, lr_cpitch, stream_ptr())
-            K.conv3x3_tc(self.a[c0:c1], self.l_t1.wpk, self.l_t1.bias, u1, cout=64, act=ACT_RELU, mode=1)
-            K.conv3x3_tc(u1, self.l_t2.wpk, self.l_t2.bias, u2, cout=64, act=ACT_RELU, mode=1)
-            K.conv3x3_tc(u2, self.l_out.wpk, self.l_out.bias, None, cout=16, act=ACT_NONE, out_f32=self.out[c0:c1],
-                         res_f32=bic, post=(2.0, -1.0))
-            if after_chunk is not None:
-                after_chunk(c0, c1)
-
-    def run(self, lr_f32, lr_cpitch=3, bicubic=True, after_chunk=None):
+    def run(self, lr_f32, lr_cpitch=3, bicubic=True):
         """x_in must already hold the packed input; lr_f32: fp32 tensor whose first 3 channels are LR RGB
-        (bicubic=False: the caller has already issued run_bicubic, e.g. on another stream).
-        after_chunk(c0, c1): called once per finished range of clips [c0, c1) of self.out (whole batch when not chunked)."""
+        (bicubic=False: the caller has already issued run_bicubic, e.g. on another stream)."""
         B, h, w = self.B, self.h, self.w
-        chunked = bool(self.chunk) and bicubic
-        if bicubic and not chunked:
+        if bicubic:
             self.run_bicubic(lr_f32, lr_cpitch)
         if self.lin:
             K.conv3x3_lin_chain(self.x_in, self.a, self.b, self.trunk_w, self.trunk_b, self.trunk_plan)
@@ -179,16 +153,11 @@ class GeneratorPlan:
             for c1, c2 in self.l_res:
                 K.conv3x3_tc(self.a, c1.wpk, c1.bias, self.b, cout=64, act=ACT_RELU)
                 K.conv3x3_tc(self.b, c2.wpk, c2.bias, self.a, cout=64, act=ACT_NONE, res=self.a)
-        if chunked:
-            self._tail_chunked(lr_f32, lr_cpitch, after_chunk)
-            return self.out
         K.conv3x3_tc(self.a, self.l_t1.wpk, self.l_t1.bias, self.u1, cout=64, act=ACT_RELU, mode=1)
         K.conv3x3_tc(self.u1, self.l_t2.wpk, self.l_t2.bias, self.u2, cout=64, act=ACT_RELU, mode=1)
         # output stage: conv(64->3) + bicubic_four(LR), then preprocess (*2-1): lib/frvsr.py:79-87
         K.conv3x3_tc(self.u2, self.l_out.wpk, self.l_out.bias, None, cout=16, act=ACT_NONE, out_f32=self.out,
                      res_f32=self.bic, post=(2.0, -1.0))
-        if after_chunk is not None:
-            after_chunk(0, B)
         return self.out
 
 

@@ -160,3 +160,21 @@ def test_metrics_crop_window_matches_reference_crop_8x8_golden():
         c, y, x = crop_8x8(t)
         assert c.shape[:2] == tuple(int(v) for v in g["crop%d" % i][2:])
     assert crop_window(144, 180) == (8, 10, 128, 160) and crop_window(32, 32)[2:] == (0, 0)
+
+
+def test_adam_step_counts_from_a_reference_checkpoint():
+    """Resuming from a checkpoint written by the reference: TensorFlow stores beta1^(t+1) per optimiser under
+    generator_train/beta1_power{,_1,_2} (discriminator, generator, fnet); the discriminator stepped only withD_counter times."""
+    from types import SimpleNamespace
+    from tecogan_b200.lib.Teco import _TrainState
+    ck = {"generator_train/beta1_power": 0.9 ** (37 + 1), "generator_train/beta1_power_1": 0.9 ** (100 + 1),
+          "generator_train/beta1_power_2": 0.9 ** (100 + 1), "generator_train/gen_train_with_D_counter": 37}
+    me = SimpleNamespace(GAN=True, global_step=100)
+    opt = SimpleNamespace(b1=0.9)
+    steps = {tag: _TrainState._tf_adam_steps(me, ck.get, tag, opt) for tag in "gfd"}
+    assert steps == {"g": 100, "f": 100, "d": 37}
+    only_counter = {"generator_train/gen_train_with_D_counter": 12}
+    assert _TrainState._tf_adam_steps(me, only_counter.get, "d", opt) == 12
+    assert _TrainState._tf_adam_steps(me, {}.get, "d", opt) == 100          # nothing known: every optimiser at global_step
+    frvsr = SimpleNamespace(GAN=False, global_step=5)
+    assert _TrainState._tf_adam_steps(frvsr, {"generator_train/beta1_power_1": 0.9 ** 6}.get, "f", opt) == 5
