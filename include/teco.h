@@ -189,7 +189,7 @@ int teco_f32_to_bf16_rowpad(const float* src, void* dst, int64_t npix, int32_t C
 /* save_img quantisation lib/ops.py:521-523: clip(x*255,0,255) -> uint8 (truncation), RGB order kept. */
 int teco_to_u8(const float* x, uint8_t* y, int64_t n, void* stream);
 /* deprocess + save_img in one pass (reference lib/ops.py:17-22 and 521-523): y01 = (x + 1) / 2 and y8 = u8(clip(255 * y01)).
-   Bit-identical to teco_affine_act_f32(0.5, 0.5) followed by teco_to_u8. */
+   Bit-identical to teco_affine_act_f32(0.5, 0.5) followed by teco_to_u8.  y01 may be NULL (uint8 frame only). */
 int teco_deprocess_u8(const float* x, float* y01, uint8_t* y8, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -70,7 +70,7 @@ __global__ void deprocess_u8_kernel(const float* __restrict__ x, float* __restri
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     float4 o;
     o.x = 0.5f * v.x + 0.5f; o.y = 0.5f * v.y + 0.5f; o.z = 0.5f * v.z + 0.5f; o.w = 0.5f * v.w + 0.5f;
-    reinterpret_cast<float4*>(y01)[i] = o;
+    if (y01) reinterpret_cast<float4*>(y01)[i] = o;
     uchar4 q;
     q.x = (uint8_t)fminf(fmaxf(o.x * 255.0f, 0.f), 255.f); q.y = (uint8_t)fminf(fmaxf(o.y * 255.0f, 0.f), 255.f);
     q.z = (uint8_t)fminf(fmaxf(o.z * 255.0f, 0.f), 255.f); q.w = (uint8_t)fminf(fmaxf(o.w * 255.0f, 0.f), 255.f);
@@ -79,7 +79,7 @@ __global__ void deprocess_u8_kernel(const float* __restrict__ x, float* __restri
   if (blockIdx.x == 0 && threadIdx.x < (int)(n - 4 * n4)) {   // tail (n not a multiple of 4)
     const long long i = 4 * n4 + threadIdx.x;
     const float o = 0.5f * x[i] + 0.5f;
-    y01[i] = o;
+    if (y01) y01[i] = o;
     y8[i] = (uint8_t)fminf(fmaxf(o * 255.0f, 0.f), 255.f);
   }
 }
@@ -320,7 +320,7 @@ int teco_to_u8(const float* x, uint8_t* y, int64_t n, void* stream) {
 }
 
 int teco_deprocess_u8(const float* x, float* y01, uint8_t* y8, int64_t n, void* stream) {
-  TECO_CHECK_ARG(x && y01 && y8 && n > 0, "teco_deprocess_u8: bad argument");
+  TECO_CHECK_ARG(x && y8 && n > 0, "teco_deprocess_u8: bad argument");   // y01 may be NULL: uint8 frame only
   TECO_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)y01) & 15) == 0 && (((uintptr_t)y8) & 3) == 0,
                  "teco_deprocess_u8: x / y01 must be 16-byte aligned, y8 4-byte aligned");
   const long long n4 = n / 4;

@@ -13,6 +13,8 @@ Look-ahead (bf16 mode, step(lr, next_lr=...) / run_sequence): the flow of frame 
 runs concurrently with generator_F of frame i; frame i+1 then starts directly with warp + generator.  Same kernels on
 the same inputs in the same order per buffer, hence bit-identical outputs to the serial recurrence (tested).
 """
+import os
+
 import torch
 
 from . import config
@@ -262,7 +264,10 @@ class ClipEngine:
     contiguous block) -> self.clip_u8 [T,B,4h,4w,3] uint8 (save_img quantisation, lib/ops.py:521-523); the fp32 output of
     the last frame stays in self.out01."""
 
-    def __init__(self, h, w, T, num_resblock=16, batch=1, use_graph=True, device="cuda"):
+    def __init__(self, h, w, T, num_resblock=16, batch=1, use_graph=True, device="cuda", fnet_pairs=None):
+        """fnet_pairs: consecutive frame pairs (of all B clips) per fnet pass -- a divisor of T-1.  All pairs of a clip are
+        independent (lib/Teco.py:102-117 batches them all); more pairs per pass = fewer, larger launches.  Default:
+        TECO_FNET_PAIRS or 1."""
         if h < 8 or w < 8:
             raise ValueError("ClipEngine: LR frames must be at least 8x8")
         if T < 1:
@@ -280,18 +285,24 @@ class ClipEngine:
             self.gen = GeneratorPlan(gs, batch, h, w, num_resblock, self.device)
         with variable_scope('fnet'), variable_scope('autoencode_unit') as fs:
             _ensure_vars_fnet()
-            self.fnet = FNetPlan(fs, batch, h, w, self.device)
-        self.flows = torch.zeros((max(T - 1, 1),) + tuple(self.fnet.flow.shape), device=self.device, dtype=f32)
+            if fnet_pairs is None:
+                fnet_pairs = int(os.environ.get("TECO_FNET_PAIRS", "1"))
+            if T > 1 and (fnet_pairs < 1 or (T - 1) % fnet_pairs):
+                raise ValueError("ClipEngine: fnet_pairs=%d does not divide the %d frame pairs of a clip" % (fnet_pairs, T - 1))
+            self.pairs = fnet_pairs if T > 1 else 1
+            self.fnet = FNetPlan(fs, batch * self.pairs, h, w, self.device)
+        self.flows = torch.zeros((max(T - 1, 1), batch) + tuple(self.fnet.flow.shape[1:]), device=self.device, dtype=f32)
         self.graph = None
-        # our kernel launches per clip batch: fnet pairs, then per frame warp/pack/generator/deprocess
-        self.launches = (T - 1) * (self.fnet.launches + 2) + T * (self.gen.launches + 2) + (T - 1)
+        # our kernel launches per clip batch: fnet passes, then per frame warp/pack/generator/deprocess
+        self.launches = ((T - 1) // self.pairs) * (self.fnet.launches + 2) + T * (self.gen.launches + 2) + (T - 1)
 
     def _body(self):
         g, f, T = self.gen, self.fnet, self.T
-        for t in range(1, T):
-            _f32_slice_to_bf16(self.clip_in[t - 1], 0, 3, f.x_in, 0)
-            _f32_slice_to_bf16(self.clip_in[t], 0, 3, f.x_in, 3)
-            f.run(flow_out=self.flows[t - 1])
+        P, hw3 = self.pairs, (self.h, self.w, 3)
+        for t in range(1, T, P):                # pairs (t-1, t) .. (t+P-2, t+P-1): time-major, so P frames are one block
+            _f32_slice_to_bf16(self.clip_in[t - 1:t - 1 + P].view(-1, *hw3), 0, 3, f.x_in, 0)
+            _f32_slice_to_bf16(self.clip_in[t:t + P].view(-1, *hw3), 0, 3, f.x_in, 3)
+            f.run(flow_out=self.flows[t - 1:t - 1 + P].view((-1,) + tuple(self.flows.shape[2:])))
         n = self.out01.numel()
         for t in range(T):
             if t == 0:
@@ -300,7 +311,7 @@ class ClipEngine:
                 K.warp_s2d_fused(g.out, self.flows[t - 1], g.x_in, S2D_OFF, in_scale=0.5, in_shift=0.5)
             _f32_slice_to_bf16(self.clip_in[t], 0, 3, g.x_in, LR_OFF)
             g.run(self.clip_in[t], 3)
-            call("teco_deprocess_u8", ptr(g.out, f32), ptr(self.out01, f32), ptr(self.clip_u8[t], torch.uint8), n, stream_ptr())
+            call("teco_deprocess_u8", ptr(g.out, f32), ptr(self.out01 if t == T - 1 else None, f32), ptr(self.clip_u8[t], torch.uint8), n, stream_ptr())
 
     def replay(self):
         """Process the clip batch already in self.clip_in."""
