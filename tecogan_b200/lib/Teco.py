@@ -147,6 +147,10 @@ class _Graph:
         dt_ratio = min(FLAGS.Dt_ratio_max, FLAGS.Dt_ratio_0 + FLAGS.Dt_ratio_add * float(global_step))
         if GAN_Flag:  # :180-313
             if not FLAGS.Dt_mergeDs:
+                # The reference's own non-merged branch cannot run either: lib/Teco.py:248,269 bind the (net, layer_list)
+                # TUPLE that discriminator_F returns (lib/Teco.py:74) to tdiscrim_*_output, and the layer loss (:290) reads
+                # real_layers / fake_layers that only the merged branch defines.  (Fix_margin, lib/Teco.py:283, is a constant
+                # 0.0, not a flag: its hinge term is dead code in the reference.)
                 raise ValueError("TecoGAN: only the merged spatio-temporal discriminator (Dt_mergeDs, config of record "
                                  "runGan.py:215) is built")
             t_size = 3 * (T // 3)

@@ -10,3 +10,4 @@ timeout 800 python bench.py --steps 10 --warmup 3 > gpurun_out/c3_bench.json 2> 
 tail -10 gpurun_out/c3_bench.err; head -c 400 gpurun_out/c3_bench.json
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:warp_s2d_v2 --launch-skip 2 --launch-count 1 -o gpurun_out/r02_warp_v2b python tools/profile_warp.py > gpurun_out/ncu_warp.log 2>&1; echo "ncu warp rc=$?"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_launches_clip296_b.csv python tools/profile_clip.py > gpurun_out/ncu_clip.log 2>&1; echo "ncu list rc=$?"
+TECO_TRAIN_PROFILE=1 TECO_TRAIN_NOGRAPH=1 TECO_TRAIN_PRECISION=bf16 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_launches_train_frvsr.csv python tools/bench_train.py frvsr > gpurun_out/ncu_train.log 2>&1; echo "ncu train rc=$?"
