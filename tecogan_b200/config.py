@@ -1,5 +1,8 @@
 """Run-time configuration of the compute path (not part of the reference interface)."""
-_cfg = {"precision": "bf16", "train_precision": "fp32", "lin_trunk": __import__("os").environ.get("TECO_LIN_TRUNK", "1") == "1"}
+import os as _os
+
+_cfg = {"precision": "bf16", "train_precision": "fp32", "lin_trunk": _os.environ.get("TECO_LIN_TRUNK", "1") == "1",
+        "train_tc_all": _os.environ.get("TECO_TRAIN_TC_ALL", "1") == "1"}
 
 
 def set_precision(p):
@@ -38,3 +41,9 @@ def set_lin_trunk(on):
 
 def lin_trunk():
     return _cfg["lin_trunk"]
+
+
+def train_tc_all():
+    """bf16 training mode: also run conv2_tran (forward, input and weight gradient) and the narrow-output convolutions
+    (generator 64 -> 3, fnet 32 -> 2) on tcgen05 instead of the fp32 kernels (TECO_TRAIN_TC_ALL=0 restores the latter)."""
+    return _cfg["train_tc_all"]

@@ -635,10 +635,17 @@ class _Conv3x3TC(torch.autograd.Function):
             raise ValueError("conv2d: fused activation and residual are mutually exclusive")
         Cin, Cout = w.shape[2], w.shape[3]
         cip, cop = _pad64(Cin), _pad64(Cout)
-        wpk, bp = _tc_packed(w, b, 0, cip, cop)
         xb = _to_bf16_rows(x, cip)
-        yb = conv3x3_tc(xb, wpk, bp, cout=cop, act=act)
-        y = _from_bf16_rows(yb, Cout, None if res is None else _cc(res))
+        if Cout < 16 and res is None:
+            # narrow output (generator 64 -> 3, fnet 32 -> 2): the fp32-output stage of the inference path -- the network's
+            # output is not rounded to bf16
+            wpk, bp = _tc_packed(w, b, 0, cip, 16)
+            y = torch.empty(x.shape[:3] + (Cout,), device=x.device, dtype=f32)
+            conv3x3_tc(xb, wpk, bp, None, cout=16, act=act, out_f32=y)
+        else:
+            wpk, bp = _tc_packed(w, b, 0, cip, cop)
+            yb = conv3x3_tc(xb, wpk, bp, cout=cop, act=act)
+            y = _from_bf16_rows(yb, Cout, None if res is None else _cc(res))
         ctx.cfg = (act, b is not None, res is not None)
         # the bf16 copy of x feeds the tensor-core weight gradient (half the bytes of the fp32 activation)
         ctx.save_for_backward(xb if ctx.needs_input_grad[1] else None, w, y if act != ACT_NONE else None)
@@ -662,12 +669,14 @@ class _Conv3x3TC(torch.autograd.Function):
             dxb = conv3x3_tc(dzb, wpk_t, None, cout=cip, act=ACT_NONE)
             dx = _from_bf16_rows(dxb, Cin)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
             if Cout % 4 == 0:
+                dw = torch.empty_like(w)
                 conv3x3_wgrad_tc(xb, dzb, dw, Cin, Cout)          # tcgen05, pixels as the contraction dimension
-            else:   # 16-byte atomics need Cout % 4 == 0: fp32 kernel on the widened bf16 activation
-                N, H, W, _ = xb.shape
-                conv2d_wgrad_raw(bf16_to_f32(xb, Cin), dz, dw, None, stride=1, pad_t=1, pad_l=1, OH=H, OW=W)
+            else:   # 16-byte atomics need Cout % 4 == 0 (generator 64->3, fnet 32->2): dW with Cout rounded up to 4 --
+                c4 = (Cout + 3) // 4 * 4                          # the extra columns see the zero pad channels of dzb
+                dw4 = torch.empty(w.shape[:3] + (c4,), device=w.device, dtype=f32)
+                conv3x3_wgrad_tc(xb, dzb, dw4, Cin, c4)
+                dw = dw4[..., :Cout].contiguous()
             if has_b and ctx.needs_input_grad[2]:
                 db = bias_grad(dz)
         return dx, dw, db, None, (dy if has_res else None)
@@ -675,3 +684,79 @@ class _Conv3x3TC(torch.autograd.Function):
 
 def conv3x3_train_tc(x, w, b=None, act=ACT_NONE, res=None):
     return _Conv3x3TC.apply(x, w, b, act, res)
+
+
+# conv2_tran in bf16 training mode.  y[2j + ky] += x[j] w[ky], so with dz in space-to-depth form
+# dzs[j][(py, px, co)] = dz[2j + py, 2i + px][co] both gradients are ordinary 3x3 stride-1 SAME problems on the LR grid:
+#   ky = 0 -> (row offset 0, phase 0), ky = 1 -> (0, 1), ky = 2 -> (+1, 0)          (columns alike)
+#   dx[p][ci]  = sum over taps (1+dj, 1+di), c' of dzs[p + (dj, di)][c'] W'[1+dj, 1+di, c', ci]      -> teco_conv3x3_tc
+#   dW'[1+dj, 1+di, c', ci] = sum_p dzs[p + (dj, di)][c'] x[p][ci]                                    -> teco_conv3x3_wgrad_tc
+# with W'[1+dj(ky), 1+di(kx), (py(ky), px(kx), co), ci] = w[ky, kx, co, ci] and zero elsewhere.
+_TCONV_TAP = ((0, 0), (0, 1), (1, 0))         # ky -> (offset, phase)
+_tconv_idx = {}
+
+
+def _tconv_index(device):
+    """Row of the [36, C, C] view of W' = [ty, tx, phase] that holds w[ky, kx] (ky-major), as a device tensor."""
+    t = _tconv_idx.get(device)
+    if t is None:
+        rows = []
+        for ky in range(3):
+            for kx in range(3):
+                (dj, py), (di, px) = _TCONV_TAP[ky], _TCONV_TAP[kx]
+                rows.append(((1 + dj) * 3 + (1 + di)) * 4 + py * 2 + px)
+        t = _tconv_idx[device] = torch.tensor(rows, device=device, dtype=torch.int64)
+    return t
+
+
+class _ConvTranspose2xTC(torch.autograd.Function):
+    """conv2_tran() 64 -> 64 on tcgen05: forward = the 4-phase kernel of the inference path (teco_conv3x3_tc mode 1), input and
+    weight gradients through the space-to-depth identities above.  Reference lib/ops.py:35-44 and its TF autodiff."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x, w = _cc(x), _cc(w)
+        Cout, Cin = w.shape[2], w.shape[3]
+        wpk, bp = _tc_packed(w, b, 1, Cin, Cout)                  # flag 1: conv_transpose layout [kh,kw,Cout,Cin]
+        xb = _to_bf16_rows(x, Cin)
+        yb = conv3x3_tc(xb, wpk, bp, cout=Cout, act=act, mode=1)
+        y = _from_bf16_rows(yb, Cout)
+        ctx.cfg = (act, b is not None)
+        ctx.save_for_backward(xb, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        act, has_b = ctx.cfg
+        xb, w, y = ctx.saved_tensors
+        dy = _cc(dy)
+        dz = dy
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("teco_act_bwd_f32", ptr(y, f32), ptr(dy, f32), ptr(dz, f32), dy.numel(), act, stream_ptr())
+        N, H2, W2, Cout = dz.shape
+        H, W, Cin = H2 // 2, W2 // 2, w.shape[3]
+        dzb = _to_bf16_rows(dz, Cout)
+        dzs = dzb.view(N, H, 2, W, 2, Cout).permute(0, 1, 3, 2, 4, 5).reshape(N, H, W, 4 * Cout)   # one copy: (py, px, co)
+        idx = _tconv_index(w.device)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            key = (w.data_ptr(), tuple(w.shape), "tconv_dgrad")
+            wpk2 = _tc_wcache.get(key)
+            if wpk2 is None:
+                wp = torch.zeros((36, Cout, Cin), device=w.device, dtype=f32)
+                wp.index_copy_(0, idx, w.detach().reshape(9, Cout, Cin))
+                wpk2 = _tc_wcache[key] = packed_weight(wp.view(3, 3, 4 * Cout, Cin), 4 * Cout, Cin, 0)
+            dxb = conv3x3_tc(dzs, wpk2, None, cout=Cin, act=ACT_NONE)
+            dx = _from_bf16_rows(dxb, Cin)
+        if ctx.needs_input_grad[1]:
+            dwp = torch.empty((3, 3, 4 * Cout, Cin), device=w.device, dtype=f32)
+            conv3x3_wgrad_tc(dzs, xb, dwp, 4 * Cout, Cin)        # dzs is the shifted operand, x the unshifted one
+            dw = dwp.view(36, Cout, Cin).index_select(0, idx).view(3, 3, Cout, Cin)
+            if has_b and ctx.needs_input_grad[2]:
+                db = bias_grad(dz)
+        return dx, dw, db, None
+
+
+def conv_transpose2x_train_tc(x, w, b=None, act=ACT_NONE):
+    return _ConvTranspose2xTC.apply(x, w, b, act)
