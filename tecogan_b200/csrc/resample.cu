@@ -660,8 +660,6 @@ int teco_warp_bwd_f32(const float* img, const float* flow, const float* dout, fl
 bool teco_warp_s2d_v2_applicable(const void* dst, int dst_cpitch, int ch_off, int dst_bf16, const float* warped_out);
 int teco_warp_s2d_v2_launch(const float* pre_gen, const float* flow_lr, void* dst, int N, int h, int w, int fh, int fw,
                             int dst_cpitch, int ch_off, float in_scale, float in_shift, cudaStream_t stream);
-int teco_warp_s2d_v3_launch(const float* pre_gen, const float* flow_lr, void* dst, int N, int h, int w, int fh, int fw,
-                            int dst_cpitch, int ch_off, float in_scale, float in_shift, cudaStream_t stream);
 extern "C" {
 
 int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, float* warped_out, int32_t N, int32_t h,
@@ -673,12 +671,10 @@ int teco_warp_s2d_fused(const float* pre_gen, const float* flow_lr, void* dst, f
   TECO_CHECK_ARG(ch_off >= 0 && ch_off + 48 <= dst_cpitch, "teco_warp_s2d_fused: 48 channels do not fit at ch_off=%d in pitch %d",
                  ch_off, dst_cpitch);
   TECO_CHECK_ARG((((uintptr_t)pre_gen) & 15) == 0, "teco_warp_s2d_fused: pre_gen must be 16-byte aligned");
-  // A/B switch, read per call: TECO_WARP_V2 = 0 first version, 2 second (one window per 4x32 tile), default third (pipelined)
-  const char* v2_env = getenv("TECO_WARP_V2");
-  const int ver = !v2_env ? 3 : (v2_env[0] == '0' ? 1 : (v2_env[0] == '2' ? 2 : 3));
-  if (ver > 1 && teco_warp_s2d_v2_applicable(dst, dst_cpitch, ch_off, dst_bf16, warped_out))
-    return (ver == 2 ? teco_warp_s2d_v2_launch : teco_warp_s2d_v3_launch)(pre_gen, flow_lr, dst, N, h, w, fh, fw, dst_cpitch, ch_off,
-                                                                        in_scale, in_shift, (cudaStream_t)stream);
+  const char* v2_env = getenv("TECO_WARP_V2");                 // A/B switch, read per call: "0" selects the first version
+  if ((!v2_env || v2_env[0] != '0') && teco_warp_s2d_v2_applicable(dst, dst_cpitch, ch_off, dst_bf16, warped_out))
+    return teco_warp_s2d_v2_launch(pre_gen, flow_lr, dst, N, h, w, fh, fw, dst_cpitch, ch_off, in_scale, in_shift,
+                                   (cudaStream_t)stream);
   const int tiles_x = teco_ceil_div(w, WS_TLW), tiles_y = teco_ceil_div(h, WS_TLH);
   TECO_CHECK_ARG(tiles_y <= 65535 && N <= 65535, "teco_warp_s2d_fused: more than 65535 row bands or images");
   const size_t smem = WS_SMEM_FLOATS * sizeof(float);

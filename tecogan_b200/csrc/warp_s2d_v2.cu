@@ -277,151 +277,6 @@ warp_s2d_v2_kernel(const float* __restrict__ pre_gen, const float* __restrict__ 
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------------
-// Third version: the same per-pixel code, software-pipelined.  ncu of the second version: instructions per pixel had halved,
-// the time had not -- every CTA spends most of its life waiting (flow samples from L2, then the window from DRAM, then the
-// barrier), and with 4 CTAs per SM there is too little other work to cover it (barrier stalls 4.2 per issued instruction).
-// Here a CTA owns a band of V3_TR LR rows x 32 LR columns and walks it in sub-tiles of 2 LR rows (8 x 128 HR pixels, 4 per
-// thread); the source windows go through a ring of two 20 KB buffers, the bulk copies of sub-tile s+2 are issued by warp 0 as
-// soon as sub-tile s has left its buffer, so from the second sub-tile on the window is already there when the CTA needs it;
-// the staging tile is double-buffered too, so the 16-byte stores of sub-tile s overlap the pixel loop of sub-tile s+1.
-// One __syncthreads per sub-tile.
-constexpr int V3_TR = 8;                                     // LR rows per CTA (4 sub-tiles)
-constexpr int V3_NSUB = V3_TR / 2;
-constexpr int V3_WIN_FLOATS = 5 * 1024;                      // per ring buffer: 12 rows x 140 px of fp32 RGB
-constexpr int V3_STAGE_BYTES = 2 * V2_TLW * 96;              // per staging buffer: 2 LR rows
-constexpr int V3_NSAMP = (V3_TR + 1) * (V2_TLW + 1);         // 297 flow samples
-
-struct V3Smem {
-  float2 flow[V3_NSAMP + 1];
-  unsigned long long bar[2];      // one mbarrier per window buffer
-  int win[2][6];                  // per ring slot: y_lo, x_lo, rows, floats per window row, flags
-};
-
-// warp 0: window of sub-tile s (LR rows 2s, 2s+1 of the band) from the three flow-sample rows around it; parameters into ring
-// slot s & 1, bulk copies into window buffer s & 1.
-__device__ __forceinline__ void v3_prepare(V3Smem& S, int s, const float* img, float* winbuf, int Y0, int X0, int H, int W, int lane) {
-  int kmin_y = 0x7fffffff, kmax_y = (int)0x80000000, kmin_x = 0x7fffffff, kmax_x = (int)0x80000000;
-  constexpr int n = 3 * (V2_TLW + 1);                        // 99 samples
-#pragma unroll
-  for (int i = 0; i < (n + 31) / 32; ++i) {
-    const float2 f = S.flow[2 * s * (V2_TLW + 1) + min(lane + 32 * i, n - 1)];
-    const int ky = f2key(f.x), kx = f2key(f.y);
-    kmin_y = min(kmin_y, ky);
-    kmax_y = max(kmax_y, ky);
-    kmin_x = min(kmin_x, kx);
-    kmax_x = max(kmax_x, kx);
-  }
-  const float mny = key2f(__reduce_min_sync(0xffffffffu, kmin_y)), mxy = key2f(__reduce_max_sync(0xffffffffu, kmax_y));
-  const float mnx = key2f(__reduce_min_sync(0xffffffffu, kmin_x)), mxx = key2f(__reduce_max_sync(0xffffffffu, kmax_x));
-  const V2Window v = v2_window(mny, mxy, mnx, mxx, Y0 + 8 * s, 8, X0, H, W, V3_WIN_FLOATS);
-  if (lane == 0) {
-    int* w = S.win[s & 1];
-    w[0] = v.y_lo; w[1] = v.x_lo; w[2] = v.rows; w[3] = v.rowf; w[4] = v.flags;
-  }
-  if (v.flags & 1) v2_stage(img, W, v, winbuf + (s & 1) * V3_WIN_FLOATS, tcptx::smem_u32(&S.bar[s & 1]), lane);
-}
-
-__global__ void __launch_bounds__(V2_TPB, 4)
-warp_s2d_v3_kernel(const float* __restrict__ pre_gen, const float* __restrict__ flow_lr, __nv_bfloat16* __restrict__ dst,
-                   int h, int w, int fh, int fw, int dst_cpitch, int ch_off, float in_scale, float in_shift) {
-  extern __shared__ __align__(16) unsigned char v3_smem[];
-  float* win = reinterpret_cast<float*>(v3_smem);                                  // 2 x V3_WIN_FLOATS
-  unsigned char* stage = v3_smem + 2 * V3_WIN_FLOATS * sizeof(float);              // 2 x V3_STAGE_BYTES
-  V3Smem& S = *reinterpret_cast<V3Smem*>(stage + 2 * V3_STAGE_BYTES);
-  const int H = 4 * h, W = 4 * w;
-  const int n = blockIdx.z, ly0 = blockIdx.y * V3_TR, lx0 = blockIdx.x * V2_TLW;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const float* img = pre_gen + (size_t)n * H * W * 3;
-  const int Y0 = 4 * ly0, X0 = 4 * lx0;
-  const int nsub = min(V3_NSUB, (h - ly0 + 1) >> 1);        // sub-tiles that hold at least one row of the image
-
-  if (tid == 0) {
-    tcptx::mbar_init(tcptx::smem_u32(&S.bar[0]), 1);
-    tcptx::mbar_init(tcptx::smem_u32(&S.bar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  {
-    const float* fb = flow_lr + (size_t)n * fh * fw * 2;
-    for (int sidx = tid; sidx < V3_NSAMP; sidx += V2_TPB) {
-      const int r = sidx / (V2_TLW + 1), j = sidx - r * (V2_TLW + 1);
-      const int i = min(ly0 + r, h - 1), jj = min(lx0 + j, w - 1);            // upscale_four replicates the last row / column
-      const int si = i < fh ? i : 2 * fh - 1 - i, sj = jj < fw ? jj : 2 * fw - 1 - jj;   // tf.pad SYMMETRIC, main.py:212
-      float2 f = *reinterpret_cast<const float2*>(fb + (si * fw + sj) * 2);
-      f.x *= 4.f;
-      f.y *= 4.f;
-      S.flow[sidx] = f;
-    }
-  }
-  __syncthreads();
-  if (wid == 0) {
-    v3_prepare(S, 0, img, win, Y0, X0, H, W, lane);
-    if (nsub > 1) v3_prepare(S, 1, img, win, Y0, X0, H, W, lane);
-  }
-
-  const int xl = tid & (4 * V2_TLW - 1), rh = tid >> 7;
-  const int lxl = xl >> 2, dx = xl & 3;
-  const float wx1 = 0.25f * (float)dx, wx0 = 1.f - wx1;
-  V2Thread t;
-  t.hy = (float)(H - 2);
-  t.hx = (float)(W - 2);
-  t.Xf = (float)(X0 + xl);
-  t.in_scale = in_scale;
-  t.in_shift = in_shift;
-  unsigned char* dtile = reinterpret_cast<unsigned char*>(dst) + 2 * ((((size_t)n * h + ly0) * w + lx0) * dst_cpitch + ch_off);
-  const int rpitch = w * dst_cpitch * 2, ppitch = dst_cpitch * 2;
-  __syncthreads();
-
-  uint32_t phases = 0;           // bit b: parity of the next completion of window buffer b's mbarrier
-#pragma unroll 1
-  for (int s = 0; s < nsub; ++s) {
-    const int b = s & 1;
-    V2Window v;
-    {
-      const int* wp = S.win[b];
-      v.y_lo = wp[0]; v.x_lo = wp[1]; v.rows = wp[2]; v.rowf = wp[3]; v.flags = wp[4];
-    }
-    const bool staged = v.flags & 1;
-    const int lr = 2 * s + rh;                               // this thread's LR row of the band
-    float Gy[2], Gx[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const float2 a = S.flow[(lr + r) * (V2_TLW + 1) + lxl], c = S.flow[(lr + r) * (V2_TLW + 1) + lxl + 1];
-      Gy[r] = a.x * wx0 + c.x * wx1;
-      Gx[r] = a.y * wx0 + c.y * wx1;
-    }
-    v2_set_base(t, staged, v, W);
-    const float Yf = (float)(Y0 + 4 * lr);
-    unsigned char* srow = stage + b * V3_STAGE_BYTES + (rh * V2_TLW + lxl) * 96 + dx * 6;
-    const float* wb = win + b * V3_WIN_FLOATS;
-    if (staged) {
-      tcptx::mbar_wait_warp(tcptx::smem_u32(&S.bar[b]), (phases >> b) & 1u);   // a barrier's phase advances per STAGED use only
-      phases ^= 1u << b;
-      if ((v.flags & 6) == 6) v2_pixels<true, true, 1>(wb, t, Gy, Gx, Yf, srow);
-      else if (v.flags & 2) v2_pixels<true, false, 1>(wb, t, Gy, Gx, Yf, srow);
-      else if (v.flags & 4) v2_pixels<false, true, 1>(wb, t, Gy, Gx, Yf, srow);
-      else v2_pixels<false, false, 1>(wb, t, Gy, Gx, Yf, srow);
-    } else {
-      v2_pixels<false, false, 1>(img, t, Gy, Gx, Yf, srow);   // window too large for a ring buffer: gather through L1
-    }
-    __syncthreads();           // window buffer b and ring slot b are free, staging buffer b is complete
-    if (wid == 0 && s + 2 < nsub) {
-      tcptx::fence_async_smem();
-      v3_prepare(S, s + 2, img, win, Y0, X0, H, W, lane);
-    }
-    // staged sub-tile -> destination: 96 contiguous bytes per LR pixel as six 16-byte stores (overlaps the next pixel loop)
-    const unsigned char* sb = stage + b * V3_STAGE_BYTES;
-    for (int q = tid; q < 2 * V2_TLW * 6; q += V2_TPB) {
-      const int p = q / 6, part = q - p * 6;
-      const int r = 2 * s + (p >> 5), c = p & 31;
-      if (ly0 + r < h && lx0 + c < w) {
-        const uint4 v4 = *reinterpret_cast<const uint4*>(sb + q * 16);
-        *reinterpret_cast<uint4*>(dtile + r * rpitch + c * ppitch + part * 16) = v4;
-      }
-    }
-  }
-}
-
 }  // namespace
 
 // Called by teco_warp_s2d_fused (resample.cu) for the layouts this version covers.  Returns false when it does not apply.
@@ -442,21 +297,5 @@ int teco_warp_s2d_v2_launch(const float* pre_gen, const float* flow_lr, void* ds
   warp_s2d_v2_kernel<<<dim3((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)N), V2_TPB, smem, stream>>>(
       pre_gen, flow_lr, (__nv_bfloat16*)dst, h, w, fh, fw, dst_cpitch, ch_off, in_scale, in_shift);
   TECO_CUDA_LAUNCH_CHECK("teco_warp_s2d_fused (v2)");
-  return TECO_OK;
-}
-
-int teco_warp_s2d_v3_launch(const float* pre_gen, const float* flow_lr, void* dst, int N, int h, int w, int fh, int fw,
-                            int dst_cpitch, int ch_off, float in_scale, float in_shift, cudaStream_t stream) {
-  const size_t smem = 2 * V3_WIN_FLOATS * sizeof(float) + 2 * V3_STAGE_BYTES + sizeof(V3Smem);
-  static bool attr = false;
-  if (!attr) {
-    TECO_CUDA_CALL(cudaFuncSetAttribute(warp_s2d_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  const int tiles_x = teco_ceil_div(w, V2_TLW), tiles_y = teco_ceil_div(h, V3_TR);
-  TECO_CHECK_ARG(tiles_y <= 65535 && N <= 65535, "teco_warp_s2d_fused: more than 65535 row bands or images");
-  warp_s2d_v3_kernel<<<dim3((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)N), V2_TPB, smem, stream>>>(
-      pre_gen, flow_lr, (__nv_bfloat16*)dst, h, w, fh, fw, dst_cpitch, ch_off, in_scale, in_shift);
-  TECO_CUDA_LAUNCH_CHECK("teco_warp_s2d_fused (v3)");
   return TECO_OK;
 }

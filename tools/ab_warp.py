@@ -1,4 +1,4 @@
-"""A/B of the three versions of the fused warp + space-to-depth kernel (TECO_WARP_V2 = 0 / 2 / default, read per call) on the bench's
+"""A/B of the two versions of the fused warp + space-to-depth kernel (TECO_WARP_V2 = 0 / default, read per call) on the bench's
 HBM-sized batch (32 x 1024x1024 HR, smooth and rough motion) and on the metric-config shape (296 x 128x128 HR):
 time per launch, GB/s against the 18.5 B/HR-pixel algorithmic traffic, and the largest difference between the outputs."""
 import os
@@ -19,7 +19,7 @@ def case(name, n, h, rough):
         flow = flow + 3.0 * (torch.rand(h, h, 2, device="cuda") - 0.5)
     flow = flow.expand(n, h, h, 2).contiguous()
     outs = {}
-    for v in ("0", "2", "3"):
+    for v in ("0", "1"):
         os.environ["TECO_WARP_V2"] = v
         dst = torch.zeros(n, h, h, 64, device="cuda", dtype=torch.bfloat16)
         for _ in range(3):
@@ -34,10 +34,9 @@ def case(name, n, h, rough):
         us = e0.elapsed_time(e1) * 100.0
         gbs = n * 16 * h * h * 18.5 / (us * 1e-6) / 1e9
         outs[v] = dst.float()
-        print("%-28s v%s: %8.1f us  %7.1f GB/s" % (name, {"0": "1", "2": "2", "3": "3"}[v], us, gbs), flush=True)
-    d2, d3 = (outs["0"] - outs["2"]).abs().max().item(), (outs["0"] - outs["3"]).abs().max().item()
-    print("%-28s max |v1 - v2| = %.3e  max |v1 - v3| = %.3e  (pad channels zero: %s)" %
-          (name, d2, d3, float(outs["3"][..., 48:].abs().max()) == 0.0), flush=True)
+        print("%-28s v%s: %8.1f us  %7.1f GB/s" % (name, "2" if v == "1" else "1", us, gbs), flush=True)
+    d = (outs["0"] - outs["1"]).abs().max().item()
+    print("%-28s max |v1 - v2| = %.3e   (pad channels zero: %s)" % (name, d, float(outs["1"][..., 48:].abs().max()) == 0.0), flush=True)
 
 
 case("32x1024x1024 smooth", 32, 256, False)
