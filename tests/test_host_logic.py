@@ -178,3 +178,12 @@ def test_adam_step_counts_from_a_reference_checkpoint():
     assert _TrainState._tf_adam_steps(me, {}.get, "d", opt) == 100          # nothing known: every optimiser at global_step
     frvsr = SimpleNamespace(GAN=False, global_step=5)
     assert _TrainState._tf_adam_steps(frvsr, {"generator_train/beta1_power_1": 0.9 ** 6}.get, "f", opt) == 5
+
+
+def test_metrics_cli_lists_png_like_the_reference(tmp_path):
+    """metrics.py::listPNGinDir (reference metrics.py:28-35): only *.png, not the IB* inputs, ordered by the digits in the name."""
+    import metrics as CLI
+    for n in ("output_0010.png", "output_0002.png", "IB_0001.png", "output_0001.jpg", "col_high_0003.png", "notes.txt"):
+        (tmp_path / n).write_bytes(b"")
+    got = [p.split("/")[-1] for p in CLI.listPNGinDir(str(tmp_path))]
+    assert got == ["output_0002.png", "col_high_0003.png", "output_0010.png"]
