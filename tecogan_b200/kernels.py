@@ -696,16 +696,21 @@ _TCONV_TAP = ((0, 0), (0, 1), (1, 0))         # ky -> (offset, phase)
 _tconv_idx = {}
 
 
+def _tconv_rows():
+    """Row of the [36, C, C] view of W' = [ty, tx, phase] that holds w[ky, kx], for the nine (ky, kx) in ky-major order."""
+    rows = []
+    for ky in range(3):
+        for kx in range(3):
+            (dj, py), (di, px) = _TCONV_TAP[ky], _TCONV_TAP[kx]
+            rows.append(((1 + dj) * 3 + (1 + di)) * 4 + py * 2 + px)
+    return rows
+
+
 def _tconv_index(device):
-    """Row of the [36, C, C] view of W' = [ty, tx, phase] that holds w[ky, kx] (ky-major), as a device tensor."""
+    """_tconv_rows() as a device tensor (created once per device, outside any CUDA-graph capture: the first step is eager)."""
     t = _tconv_idx.get(device)
     if t is None:
-        rows = []
-        for ky in range(3):
-            for kx in range(3):
-                (dj, py), (di, px) = _TCONV_TAP[ky], _TCONV_TAP[kx]
-                rows.append(((1 + dj) * 3 + (1 + di)) * 4 + py * 2 + px)
-        t = _tconv_idx[device] = torch.tensor(rows, device=device, dtype=torch.int64)
+        t = _tconv_idx[device] = torch.tensor(_tconv_rows(), device=device, dtype=torch.int64)
     return t
 
 

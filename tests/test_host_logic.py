@@ -187,3 +187,80 @@ def test_metrics_cli_lists_png_like_the_reference(tmp_path):
         (tmp_path / n).write_bytes(b"")
     got = [p.split("/")[-1] for p in CLI.listPNGinDir(str(tmp_path))]
     assert got == ["output_0002.png", "col_high_0003.png", "output_0010.png"]
+
+
+def test_warp_v2_source_window_holds_every_query_of_its_tile():
+    """Host restatement of the window construction of warp_s2d_v2_kernel (csrc/warp_s2d_v2.cu::v2_window): from the min / max of
+    the 4 x flow_lr samples around a 4 x 32 LR tile it derives the rows / columns of the previous HR frame that the tile's
+    bilinear queries can touch.  Property: for random flows (smooth, rough, far out of range) and ragged frame sizes, every
+    query of every HR pixel of the tile -- floor clamped to [0, size-2] plus its +1 neighbour, as dense_image_warp does --
+    lies inside the window, and the 'interior' flags are only set when no clamp can trigger."""
+    import numpy as np
+    rng = np.random.RandomState(0)
+    TLH, TLW = 4, 32
+
+    def upscale4(f):                                   # upscale_four: legacy bilinear x4, edge-replicated (lib/ops.py:126-163)
+        h, w, _ = f.shape
+        fy = np.concatenate([f, f[-1:]], 0)
+        rows = np.stack([(1 - k / 4) * fy[:-1] + (k / 4) * fy[1:] for k in range(4)], 1).reshape(4 * h, w, 2)
+        fx = np.concatenate([rows, rows[:, -1:]], 1)
+        return np.stack([(1 - k / 4) * fx[:, :-1] + (k / 4) * fx[:, 1:] for k in range(4)], 2).reshape(4 * h, 4 * w, 2)
+
+    for case, (h, w, amp, off) in enumerate([(8, 32, 1.0, 0.0), (18, 45, 6.0, 0.0), (36, 40, 0.3, 2.5), (16, 64, 30.0, -40.0), (5, 9, 3.0, 1.0)]):
+        H, W = 4 * h, 4 * w
+        flow4 = (4.0 * (off + amp * (rng.rand(h, w, 2) - 0.5))).astype(np.float32)
+        fl = upscale4(flow4.astype(np.float64))
+        for ly0 in range(0, h, TLH):
+            for lx0 in range(0, w, TLW):
+                ii = np.minimum(np.arange(ly0, ly0 + TLH + 1), h - 1)
+                jj = np.minimum(np.arange(lx0, lx0 + TLW + 1), w - 1)
+                s = flow4[np.ix_(ii, jj)]
+                mny, mxy, mnx, mxx = s[..., 0].min(), s[..., 0].max(), s[..., 1].min(), s[..., 1].max()
+                Y0, X0 = 4 * ly0, 4 * lx0
+                qy_lo, qy_hi = Y0 - mxy, Y0 + 4 * TLH - 1 - mny
+                qx_lo, qx_hi = X0 - mxx, X0 + 4 * TLW - 1 - mnx
+                clampf = lambda v, hi: min(max(v, 0.0), hi)
+                y_lo = int(clampf(np.floor(qy_lo) - 1, H - 2))
+                y_hi = int(clampf(np.floor(qy_hi) + 1, H - 2)) + 1
+                x_lo = int(clampf(np.floor(qx_lo) - 1, W - 2)) & ~3
+                x_hi = min((int(clampf(np.floor(qx_hi) + 1, W - 2)) + 1) | 3, W - 1)
+                int_y = qy_lo >= 1 and qy_hi <= H - 3
+                int_x = qx_lo >= 1 and qx_hi <= W - 3
+                assert (x_hi - x_lo + 1) % 4 == 0 and x_lo % 4 == 0          # 16-byte aligned bulk copies of fp32 RGB rows
+                ys = np.arange(Y0, min(Y0 + 4 * TLH, H))
+                xs = np.arange(X0, min(X0 + 4 * TLW, W))
+                qy = ys[:, None] - fl[np.ix_(ys, xs)][..., 0]
+                qx = xs[None, :] - fl[np.ix_(ys, xs)][..., 1]
+                fy, fx = np.floor(qy), np.floor(qx)
+                if int_y:
+                    assert fy.min() >= 0 and fy.max() <= H - 2, (case, ly0, lx0)
+                if int_x:
+                    assert fx.min() >= 0 and fx.max() <= W - 2, (case, ly0, lx0)
+                iy, ix = np.clip(fy, 0, H - 2), np.clip(fx, 0, W - 2)
+                assert y_lo <= iy.min() and iy.max() + 1 <= y_hi, (case, ly0, lx0, y_lo, y_hi, iy.min(), iy.max())
+                assert x_lo <= ix.min() and ix.max() + 1 <= x_hi, (case, ly0, lx0, x_lo, x_hi, ix.min(), ix.max())
+
+
+def test_conv_transpose_gradients_through_the_space_to_depth_identity():
+    """kernels._ConvTranspose2xTC computes both gradients of conv2_tran as ordinary 3x3 stride-1 problems on the space-to-depth
+    form of dz (W' = zero-scattered weights, rows kernels._tconv_rows()).  The identity itself, in fp32 on the CPU with the
+    oracle's convolutions, against the oracle's autograd of conv2d_transpose (reference lib/ops.py:35-44)."""
+    import torch
+    from oracle import teco_oracle as O
+    from tecogan_b200 import kernels as K
+    torch.manual_seed(0)
+    N, H, W, C = 2, 5, 6, 4
+    x = torch.randn(N, H, W, C, requires_grad=True)
+    w = torch.randn(3, 3, C, C, requires_grad=True)             # [kh, kw, Cout, Cin]
+    y = O.conv2d_transpose(x, w, torch.randn(C))
+    dz = torch.randn_like(y)
+    y.backward(dz)
+    dzs = dz.view(N, H, 2, W, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, H, W, 4 * C)          # channel (py, px, co)
+    idx = torch.tensor(K._tconv_rows())
+    assert sorted(K._tconv_rows()) == sorted(set(K._tconv_rows())) and len(idx) == 9
+    wp = torch.zeros(36, C, C).index_copy_(0, idx, w.detach().reshape(9, C, C)).view(3, 3, 4 * C, C).requires_grad_(True)
+    dx = O.conv2d(dzs, wp, None)                                                                  # input gradient
+    assert (dx - x.grad).abs().max().item() < 1e-4
+    (dx * x.detach()).sum().backward()            # d/dW' of sum_p conv(dzs, W')[p] . x[p]  =  the wgrad kernel's sum
+    dw = wp.grad.view(36, C, C).index_select(0, idx).view(3, 3, C, C)
+    assert (dw - w.grad).abs().max().item() < 1e-4 * max(1.0, w.grad.abs().max().item())
