@@ -8,13 +8,18 @@
 // issue-bound, not memory-bound.  Here:
 //   * CTA tile 4 x 32 LR pixels (16 x 128 HR): the per-tile work (flow bound, window set-up, barriers) is paid once per 2048
 //     HR pixels instead of 1024, and the staged source window carries 2 halo rows per 16 instead of per 8;
-//   * the flow bound is four redux.sync on order-preserving integer keys + four shared atomics per warp (was 40 shuffle /
-//     min / max instructions plus a serial stage behind a second barrier); the 5 x 33 flow samples of the tile are parked in
-//     shared memory on the way, so no thread repeats the symmetric-pad index arithmetic or goes back to global memory;
+//   * the 5 x 33 flow samples of the tile are parked in shared memory once (no thread repeats the symmetric-pad index
+//     arithmetic or goes back to global memory); warp 0 bounds them with four redux.sync on order-preserving integer keys
+//     (was 40 shuffle / min / max instructions in four warps plus a serial stage), derives the source window and stages it
+//     with ONE BULK COPY PER WINDOW ROW on an mbarrier (TMA engine: no register, LSU or issue-slot cost for the window;
+//     the cp.async loop it replaced was 22 % of all instructions) while the other warps interpolate their flows;
 //   * floor() is ONE add with round-toward-minus-infinity against 1.5 * 2^23 (the sum's mantissa is the integer), the index
 //     arithmetic works directly on that bit pattern (two IMADs per pixel), clamps only on the axes whose tile can touch one;
 //   * results go through a bf16 staging tile in shared memory in destination order and leave as 16-byte stores, six per LR
-//     pixel (was: three shuffles, eight selects and an 8-byte store per HR pixel with a quarter of the lanes idle).
+//     pixel (was: three shuffles, eight selects and an 8-byte store per HR pixel with a quarter of the lanes idle);
+//   * rough motion (window larger than the 40 KB stage): the tile in two halves with their own windows, then an L1 gather.
+// Measured (profiles/r02_warp_versions_ab.txt, r02_warp_s2d_v2_32x1024_summary.txt): 239 -> 160 us on 32 x 1024x1024 HR frames
+// (0.39 -> 0.59 of the measured copy bandwidth), bit-identical output; 113 M instead of 204 M warp instructions.
 #include "teco_common.cuh"
 #include "tc_ptx.cuh"
 
